@@ -1,0 +1,470 @@
+// extern "C" layer of the B200 DBDE codec (see include/dbde_b200.h for the contracts).
+// Host-side plumbing only: geometry, scratch, launches, and the chunked pinned-staging pipeline
+// for host buffers.  No codec arithmetic lives here and there is no CPU fallback.
+#include "../../include/dbde_b200.h"
+#include "dbde_kernels.h"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace dbde;
+
+static thread_local std::string g_err;
+static int fail(int code, const char *what) {
+    g_err = what;
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char *where) {
+    g_err = std::string(where) + ": " + cudaGetErrorString(e);
+    return (int)e;
+}
+#define CK(call)                                              \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+constexpr int kHostSlots = 3;
+
+struct HostSlot {
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev = nullptr;
+    uint8_t *d_a = nullptr;      // encode: frames   | decode: stream bytes
+    uint8_t *d_b = nullptr;      // encode: records  | decode: frames
+    uint64_t *d_off = nullptr;
+    uint32_t *d_status = nullptr;
+    uint64_t *d_index = nullptr;
+    uint64_t *h_off = nullptr;   // pinned
+    size_t cap_a = 0, cap_b = 0;
+    int cap_n = 0;
+    int n = 0, first = 0;
+};
+
+struct dbde_b200_ctx {
+    int device = 0;
+    int num_sms = 0;
+    void *enc_scratch = nullptr;
+    size_t enc_scratch_bytes = 0;
+    void *dec_scratch = nullptr;
+    size_t dec_scratch_bytes = 0;
+    HostSlot slots[kHostSlots];
+    int chunk_frames = 0;
+    uint64_t launches = 0;
+};
+
+// ------------------------------------------------------------------ geometry
+static PartGeom make_geom(int W, int H, bool fast) {
+    PartGeom g;
+    g.W = W; g.H = H;
+    g.w = (W + 7) / 8; g.h = (H + 7) / 8; g.wh = g.w * g.h;
+    int ntx_max;
+    if (g.w > kTilesPerPart) {
+        g.nseg = (g.w + kTilesPerPart - 1) / kTilesPerPart;
+        g.G = 1;
+        g.ppf = g.h * g.nseg;
+        ntx_max = kTilesPerPart;
+    } else {
+        g.nseg = 1;
+        g.G = kTilesPerPart / g.w;
+        if (g.G > kMaxBandsPerPart) g.G = kMaxBandsPerPart;
+        if (g.G > g.h) g.G = g.h;
+        ntx_max = g.w;
+    }
+    auto pitch_of = [&](int ntx) { return fast ? 8 * ntx : ((8 * ntx + 15) / 16) * 16 + 32; };
+    g.pitch = pitch_of(ntx_max);
+    while (g.G > 1 && 8 * g.G * g.pitch > 20480) g.G--;
+    if (g.nseg == 1) g.ppf = (g.h + g.G - 1) / g.G;
+    int need = 8 * g.G * g.pitch;
+    if (need < 64 * kTilesPerPart) need = 64 * kTilesPerPart;
+    g.stage_bytes = ((need + 64 + 127) / 128) * 128;
+    return g;
+}
+
+static bool dims_ok(int W, int H, int nframes) {
+    if (W <= 0 || H <= 0 || nframes < 0) return false;
+    const long long wh = (long long)((W + 7) / 8) * ((H + 7) / 8);
+    return wh <= 0x0FFFFFFF && (long long)W * H <= 0x7FFFFFFFLL;
+}
+
+// where a stream should start inside a 16-byte-aligned buffer so that the first frame's U64
+// words are 16-byte aligned (record sizes are multiples of 8 when wh % 4 == 0, so every
+// payload then stays 8-byte aligned)
+static size_t payload_align_delta(int W, int H) {
+    const size_t wh = (size_t)((W + 7) / 8) * ((H + 7) / 8);
+    return (16 - (32 + 2 * wh) % 16) % 16;
+}
+
+// ------------------------------------------------------------------ lifetime
+extern "C" int dbde_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" int dbde_b200_create(int device, dbde_b200_ctx **out) {
+    if (!out) return fail(DBDE_B200_E_INVALID, "dbde_b200_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(DBDE_B200_E_NO_DEVICE, "dbde_b200: no CUDA device; this library has no CPU fallback");
+    if (device < 0 || device >= n) return fail(DBDE_B200_E_INVALID, "dbde_b200_create: device out of range");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(DBDE_B200_E_NO_DEVICE, "dbde_b200: kernels are built for sm_100a (B200) only; no fallback");
+    CK(cudaSetDevice(device));
+    dbde_b200_ctx *c = new dbde_b200_ctx();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    *out = c;
+    return 0;
+}
+
+static void free_slot(HostSlot &s) {
+    if (s.d_a) cudaFree(s.d_a);
+    if (s.d_b) cudaFree(s.d_b);
+    if (s.d_off) cudaFree(s.d_off);
+    if (s.d_status) cudaFree(s.d_status);
+    if (s.d_index) cudaFree(s.d_index);
+    if (s.h_off) cudaFreeHost(s.h_off);
+    if (s.ev) cudaEventDestroy(s.ev);
+    if (s.st) cudaStreamDestroy(s.st);
+    s = HostSlot();
+}
+
+extern "C" void dbde_b200_destroy(dbde_b200_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto &s : c->slots) free_slot(s);
+    if (c->enc_scratch) cudaFree(c->enc_scratch);
+    if (c->dec_scratch) cudaFree(c->dec_scratch);
+    delete c;
+}
+
+extern "C" const char *dbde_b200_last_error(void) { return g_err.c_str(); }
+extern "C" uint64_t dbde_b200_kernel_launches(const dbde_b200_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int dbde_b200_set_chunk_frames(dbde_b200_ctx *c, int frames) {
+    if (!c || frames < 0) return fail(DBDE_B200_E_INVALID, "set_chunk_frames: bad argument");
+    c->chunk_frames = frames;
+    return 0;
+}
+
+// ------------------------------------------------------------------ sizes
+extern "C" size_t dbde_b200_frame_record_bound(int W, int H) {
+    const size_t wh = (size_t)((W + 7) / 8) * ((H + 7) / 8);
+    return 32 + 66 * wh;
+}
+extern "C" size_t dbde_b200_stream_bound(int W, int H, int nframes) {
+    return dbde_b200_frame_record_bound(W, H) * (size_t)(nframes < 0 ? 0 : nframes) + 16;
+}
+
+// ------------------------------------------------------------------ memory helpers
+extern "C" int dbde_b200_device_alloc(dbde_b200_ctx *c, size_t bytes, void **out) {
+    if (!c || !out) return fail(DBDE_B200_E_INVALID, "device_alloc: bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMalloc(out, bytes + 32));
+    return 0;
+}
+extern "C" int dbde_b200_device_free(dbde_b200_ctx *c, void *p) {
+    if (!c) return fail(DBDE_B200_E_INVALID, "device_free: bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaFree(p));
+    return 0;
+}
+extern "C" int dbde_b200_host_alloc(size_t bytes, void **out) {
+    if (!out) return fail(DBDE_B200_E_INVALID, "host_alloc: bad argument");
+    CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return 0;
+}
+extern "C" int dbde_b200_host_free(void *p) {
+    CK(cudaFreeHost(p));
+    return 0;
+}
+extern "C" int dbde_b200_memcpy_h2d(dbde_b200_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (!c) return fail(DBDE_B200_E_INVALID, "memcpy_h2d: bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+extern "C" int dbde_b200_memcpy_d2h(dbde_b200_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (!c) return fail(DBDE_B200_E_INVALID, "memcpy_d2h: bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+static int grow(void **p, size_t *have, size_t need) {
+    if (*have >= need) return 0;
+    if (*p) CK(cudaFree(*p));
+    *p = nullptr;
+    *have = 0;
+    need += need / 4;
+    CK(cudaMalloc(p, need));
+    *have = need;
+    return 0;
+}
+
+// ------------------------------------------------------------------ device-resident hot path
+extern "C" int dbde_b200_encode_device(dbde_b200_ctx *c, const uint8_t *frames_dev, int W, int H,
+                                       uint64_t first_index, int nframes, uint8_t *out_dev, size_t out_capacity,
+                                       uint64_t *frame_offsets_dev, void *stream) {
+    if (!c || !dims_ok(W, H, nframes) || (nframes > 0 && (!frames_dev || !out_dev || !frame_offsets_dev)))
+        return fail(DBDE_B200_E_INVALID, "encode_device: bad argument");
+    if (nframes == 0) return 0;
+    if (out_capacity < dbde_b200_stream_bound(W, H, nframes) - 16)
+        return fail(DBDE_B200_E_CAPACITY, "encode_device: out_capacity < dbde_b200_stream_bound()");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool fast = (W % 16 == 0) && (H % 8 == 0) && (((uintptr_t)frames_dev & 15) == 0);
+    EncParams P;
+    P.g = make_geom(W, H, fast);
+    const unsigned long long nparts = (unsigned long long)nframes * P.g.ppf;
+    if (nparts >= 0xFFFFFFF0ull) return fail(DBDE_B200_E_INVALID, "encode_device: batch too large");
+    // scratch: [ticket | pad to 128][fstart: nframes u64][desc: nparts u64], zeroed per launch
+    const size_t sbytes = 128 + 8 * (size_t)nframes + 8 * (size_t)nparts;
+    int rc = grow(&c->enc_scratch, &c->enc_scratch_bytes, sbytes);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(c->enc_scratch, 0, sbytes, st));
+    P.frames = frames_dev;
+    P.out = out_dev;
+    P.frame_offsets = frame_offsets_dev;
+    P.ticket = (unsigned int *)c->enc_scratch;
+    P.fstart = (uint64_t *)((uint8_t *)c->enc_scratch + 128);
+    P.desc = P.fstart + nframes;
+    P.first_index = first_index;
+    P.nframes = nframes;
+    P.nparts = (unsigned)nparts;
+    CK(launch_encode(P, fast, c->num_sms, st));
+    c->launches += 1;
+    return 0;
+}
+
+extern "C" int dbde_b200_decode_device(dbde_b200_ctx *c, const uint8_t *stream_dev, size_t stream_bytes,
+                                       const uint64_t *frame_offsets_dev, int W, int H, int nframes,
+                                       uint8_t *frames_dev, uint32_t *status_dev, uint64_t *indices_dev,
+                                       void *stream) {
+    if (!c || !dims_ok(W, H, nframes) ||
+        (nframes > 0 && (!stream_dev || !frame_offsets_dev || !frames_dev || !status_dev)))
+        return fail(DBDE_B200_E_INVALID, "decode_device: bad argument");
+    if (nframes == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool fast = (W % 16 == 0) && (H % 8 == 0) && (((uintptr_t)frames_dev & 15) == 0);
+    DecParams P;
+    P.g = make_geom(W, H, fast);
+    const unsigned long long nparts = (unsigned long long)nframes * P.g.ppf;
+    if (nparts >= 0xFFFFFFF0ull) return fail(DBDE_B200_E_INVALID, "decode_device: batch too large");
+    const size_t sbytes = 4 * (size_t)nframes * ((size_t)P.g.ppf * kConsumerWarps + 1);
+    int rc = grow(&c->dec_scratch, &c->dec_scratch_bytes, sbytes);
+    if (rc) return rc;
+    P.stream = stream_dev;
+    P.stream_bytes = stream_bytes;
+    P.frame_offsets = frame_offsets_dev;
+    P.frames = frames_dev;
+    P.status = status_dev;
+    P.indices = indices_dev;
+    P.wprefix = (uint32_t *)c->dec_scratch;
+    P.nframes = nframes;
+    P.nparts = (unsigned)nparts;
+    CK(launch_decode_scan(P, st));
+    CK(launch_decode(P, fast, c->num_sms, st));
+    c->launches += 2;
+    return 0;
+}
+
+// ------------------------------------------------------------------ host-buffer hot path
+static int default_chunk(const dbde_b200_ctx *c, int W, int H, int nframes) {
+    int n = c->chunk_frames;
+    if (n <= 0) {
+        const size_t px = (size_t)W * H;
+        n = (int)((64u << 20) / (px ? px : 1));
+        if (n < 1) n = 1;
+    }
+    if (n > nframes) n = nframes;
+    return n;
+}
+
+static int ensure_slot(dbde_b200_ctx *c, HostSlot &s, size_t need_a, size_t need_b, int n) {
+    if (!s.st) CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+    if (!s.ev) CK(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+    if (s.cap_a < need_a) {
+        if (s.d_a) CK(cudaFree(s.d_a));
+        s.d_a = nullptr;
+        CK(cudaMalloc(&s.d_a, need_a));
+        s.cap_a = need_a;
+    }
+    if (s.cap_b < need_b) {
+        if (s.d_b) CK(cudaFree(s.d_b));
+        s.d_b = nullptr;
+        CK(cudaMalloc(&s.d_b, need_b));
+        s.cap_b = need_b;
+    }
+    if (s.cap_n < n) {
+        if (s.d_off) CK(cudaFree(s.d_off));
+        if (s.d_status) CK(cudaFree(s.d_status));
+        if (s.d_index) CK(cudaFree(s.d_index));
+        if (s.h_off) CK(cudaFreeHost(s.h_off));
+        s.d_off = nullptr; s.d_status = nullptr; s.d_index = nullptr; s.h_off = nullptr;
+        CK(cudaMalloc(&s.d_off, 8 * (size_t)(n + 1)));
+        CK(cudaMalloc(&s.d_status, 4 * (size_t)n));
+        CK(cudaMalloc(&s.d_index, 8 * (size_t)n));
+        CK(cudaHostAlloc(&s.h_off, 8 * (size_t)(n + 1), cudaHostAllocDefault));
+        s.cap_n = n;
+    }
+    return 0;
+}
+
+extern "C" int dbde_b200_encode_host(dbde_b200_ctx *c, const uint8_t *frames_host, int W, int H,
+                                     uint64_t first_index, int nframes, uint8_t *out_host, size_t out_capacity,
+                                     uint64_t *frame_offsets_host) {
+    if (!c || !dims_ok(W, H, nframes) || (nframes > 0 && (!frames_host || !out_host || !frame_offsets_host)))
+        return fail(DBDE_B200_E_INVALID, "encode_host: bad argument");
+    if (nframes == 0) {
+        if (frame_offsets_host) frame_offsets_host[0] = 0;
+        return 0;
+    }
+    CK(cudaSetDevice(c->device));
+    const size_t px = (size_t)W * H;
+    const int chunk = default_chunk(c, W, H, nframes);
+    const size_t delta = payload_align_delta(W, H);
+    const size_t need_a = px * chunk + 32, need_b = dbde_b200_stream_bound(W, H, chunk) + 32;
+    for (auto &s : c->slots) {
+        int rc = ensure_slot(c, s, need_a, need_b, chunk);
+        if (rc) return rc;
+    }
+    const int nchunks = (nframes + chunk - 1) / chunk;
+    size_t out_pos = 0;
+    int rc_all = 0;
+    // finish(): wait for a chunk's kernel, learn its size, queue its D2H at the running offset
+    auto finish = [&](int ci) -> int {
+        HostSlot &s = c->slots[ci % kHostSlots];
+        CK(cudaEventSynchronize(s.ev));
+        const uint64_t total = s.h_off[s.n];
+        if (out_pos + total > out_capacity) return fail(DBDE_B200_E_CAPACITY, "encode_host: out_capacity too small");
+        CK(cudaMemcpyAsync(out_host + out_pos, s.d_b + delta, total, cudaMemcpyDeviceToHost, s.st));
+        for (int i = 0; i < s.n; i++) frame_offsets_host[s.first + i] = out_pos + s.h_off[i];
+        out_pos += total;
+        return 0;
+    };
+    int pending = -1;
+    for (int ci = 0; ci < nchunks && !rc_all; ci++) {
+        HostSlot &s = c->slots[ci % kHostSlots];
+        CK(cudaStreamSynchronize(s.st));            // the slot's previous chunk has fully drained
+        s.first = ci * chunk;
+        s.n = nframes - s.first < chunk ? nframes - s.first : chunk;
+        CK(cudaMemcpyAsync(s.d_a, frames_host + px * s.first, px * s.n, cudaMemcpyHostToDevice, s.st));
+        rc_all = dbde_b200_encode_device(c, s.d_a, W, H, first_index + s.first, s.n, s.d_b + delta,
+                                         need_b - 32, s.d_off, s.st);
+        if (rc_all) break;
+        CK(cudaMemcpyAsync(s.h_off, s.d_off, 8 * (size_t)(s.n + 1), cudaMemcpyDeviceToHost, s.st));
+        CK(cudaEventRecord(s.ev, s.st));
+        if (pending >= 0) rc_all = finish(pending);
+        pending = ci;
+    }
+    if (!rc_all && pending >= 0) rc_all = finish(pending);
+    for (auto &s : c->slots)
+        if (s.st) cudaStreamSynchronize(s.st);
+    if (rc_all) return rc_all;
+    frame_offsets_host[nframes] = out_pos;
+    return 0;
+}
+
+extern "C" int dbde_b200_decode_host(dbde_b200_ctx *c, const uint8_t *stream_host, size_t stream_bytes,
+                                     const uint64_t *frame_offsets_host, int W, int H, int nframes,
+                                     uint8_t *frames_host, uint32_t *status_host, uint64_t *indices_host) {
+    if (!c || !dims_ok(W, H, nframes) ||
+        (nframes > 0 && (!stream_host || !frame_offsets_host || !frames_host || !status_host)))
+        return fail(DBDE_B200_E_INVALID, "decode_host: bad argument");
+    if (nframes == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    for (int i = 0; i < nframes; i++) {
+        const uint64_t end = i + 1 < nframes ? frame_offsets_host[i + 1] : stream_bytes;
+        if (frame_offsets_host[i] > end || end > stream_bytes)
+            return fail(DBDE_B200_E_INVALID, "decode_host: frame offsets must ascend within the stream");
+    }
+    const size_t px = (size_t)W * H;
+    const int chunk = default_chunk(c, W, H, nframes);
+    const size_t delta = payload_align_delta(W, H);
+    const int nchunks = (nframes + chunk - 1) / chunk;
+    size_t need_a = 0;
+    for (int ci = 0; ci < nchunks; ci++) {
+        const int first = ci * chunk, n = nframes - first < chunk ? nframes - first : chunk;
+        const uint64_t b0 = frame_offsets_host[first];
+        const uint64_t b1 = first + n < nframes ? frame_offsets_host[first + n] : stream_bytes;
+        if (b1 - b0 > need_a) need_a = b1 - b0;
+    }
+    need_a += 64;
+    const size_t need_b = px * chunk + 32;
+    for (auto &s : c->slots) {
+        int rc = ensure_slot(c, s, need_a, need_b, chunk);
+        if (rc) return rc;
+    }
+    // finish(): wait for a chunk's status words, then queue the D2H of its accepted frames.  A
+    // rejected frame must leave the caller's image untouched (dbde_util.cpp:296-303), so pixels
+    // come back as maximal runs of accepted frames.
+    auto finish = [&](int ci) -> int {
+        HostSlot &s = c->slots[ci % kHostSlots];
+        CK(cudaEventSynchronize(s.ev));
+        int run0 = 0;
+        for (int i = 0; i <= s.n; i++) {
+            const bool ok = i < s.n && status_host[s.first + i] == 0;
+            if (!ok) {
+                if (i > run0)
+                    CK(cudaMemcpyAsync(frames_host + px * (s.first + run0), s.d_b + px * run0, px * (size_t)(i - run0),
+                                       cudaMemcpyDeviceToHost, s.st));
+                run0 = i + 1;
+            }
+        }
+        return 0;
+    };
+    int pending = -1, rc_all = 0;
+    for (int ci = 0; ci < nchunks && !rc_all; ci++) {
+        HostSlot &s = c->slots[ci % kHostSlots];
+        CK(cudaStreamSynchronize(s.st));
+        s.first = ci * chunk;
+        s.n = nframes - s.first < chunk ? nframes - s.first : chunk;
+        const uint64_t b0 = frame_offsets_host[s.first];
+        const uint64_t b1 = s.first + s.n < nframes ? frame_offsets_host[s.first + s.n] : stream_bytes;
+        for (int i = 0; i < s.n; i++) s.h_off[i] = frame_offsets_host[s.first + i] - b0;
+        CK(cudaMemcpyAsync(s.d_off, s.h_off, 8 * (size_t)s.n, cudaMemcpyHostToDevice, s.st));
+        CK(cudaMemcpyAsync(s.d_a + delta, stream_host + b0, b1 - b0, cudaMemcpyHostToDevice, s.st));
+        rc_all = dbde_b200_decode_device(c, s.d_a + delta, b1 - b0, s.d_off, W, H, s.n, s.d_b, s.d_status,
+                                         s.d_index, s.st);
+        if (rc_all) break;
+        CK(cudaMemcpyAsync(status_host + s.first, s.d_status, 4 * (size_t)s.n, cudaMemcpyDeviceToHost, s.st));
+        if (indices_host)
+            CK(cudaMemcpyAsync(indices_host + s.first, s.d_index, 8 * (size_t)s.n, cudaMemcpyDeviceToHost, s.st));
+        CK(cudaEventRecord(s.ev, s.st));
+        if (pending >= 0) rc_all = finish(pending);
+        pending = ci;
+    }
+    if (!rc_all && pending >= 0) rc_all = finish(pending);
+    for (auto &s : c->slots)
+        if (s.st) cudaStreamSynchronize(s.st);
+    return rc_all;
+}
+
+// ------------------------------------------------------------------ host indexer
+extern "C" long dbde_b200_index_stream(const uint8_t *p, size_t bytes, int W, int H, uint64_t *offs,
+                                       long max_frames) {
+    if (!p || !offs || !dims_ok(W, H, 0)) return fail(DBDE_B200_E_INVALID, "index_stream: bad argument");
+    const size_t wh = (size_t)((W + 7) / 8) * ((H + 7) / 8);
+    const size_t fixed = 32 + 2 * wh;
+    size_t cur = 0;
+    long n = 0;
+    while (cur + fixed <= bytes && n < max_frames) {
+        uint32_t n64;
+        memcpy(&n64, p + cur + 28 + 2 * wh, 4);
+        const size_t next = cur + fixed + 8 * (size_t)n64;
+        if (next > bytes) break;
+        offs[n++] = cur;
+        cur = next;
+    }
+    offs[n] = cur;
+    return n;
+}

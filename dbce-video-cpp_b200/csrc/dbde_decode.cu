@@ -1,0 +1,356 @@
+// DBDE B200 decoder: DBDE frame records in HBM -> raw U8 frames in HBM, pixel-identical to
+// dbde_unpack_frame (dbde_util.cpp:339-345) and with its accept/reject behaviour
+// (dbde_util.cpp:295-303: a rejected frame leaves the image untouched).
+//
+// Two kernels:
+//   dbde_decode_scan_kernel : one CTA per frame. Validates the record (header tag, plane lengths,
+//                             sum(depth) == n64, depth <= 8, bounds) and turns the depth plane into
+//                             exclusive U64-word prefixes at partition-warp granularity (32 tiles),
+//                             i.e. the reference's running input pointer (dbde_util.cpp:312) made
+//                             explicit.  Reads 1 byte per tile (~1 % of the traffic).
+//   dbde_decode_kernel      : persistent, warp-specialised.  A producer warp bulk-TMAs each
+//                             partition's payload words + depth/min bytes into a ring of stages;
+//                             tile warps (one lane == one 8x8 tile) unpack with shifts and masks,
+//                             add the minimum, stage the 8-row band in shared memory and a bulk-TMA
+//                             store writes it out (generic path: cropped direct stores).
+#include "dbde_device.cuh"
+#include "dbde_kernels.h"
+
+namespace dbde {
+
+constexpr int kDecStages = 3;
+constexpr int kDecThreads = kTilesPerPart + 32;
+constexpr int kDecPayloadBytes = 64 * kTilesPerPart + 32;        // worst-case words + 16-byte hull slack
+constexpr int kDecPlaneBytes = kTilesPerPart + 32;
+constexpr int kDecStageBytes = ((kDecPayloadBytes + 2 * kDecPlaneBytes + 127) / 128) * 128;
+
+// ------------------------------------------------------------------ scan / validate pre-pass
+__device__ __forceinline__ uint32_t ldg_u32_bytes(const uint8_t *p) {
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+__global__ void __launch_bounds__(256) dbde_decode_scan_kernel(const DecParams P) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_flag;
+    const PartGeom &g = P.g;
+    const int f = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint64_t off = P.frame_offsets[f];
+    const uint64_t fixed = 32 + 2 * (uint64_t)g.wh;
+    const int nitems = g.ppf * kConsumerWarps;
+    uint32_t *wp = P.wprefix + (size_t)f * (nitems + 1);
+    if (off + fixed > P.stream_bytes) {          // cannot even read the fixed fields
+        if (tid == 0) {
+            P.status[f] = kStTruncated;
+            if (P.indices) P.indices[f] = 0;
+        }
+        return;
+    }
+    const uint8_t *rec = P.stream + off;
+    uint32_t status = 0;
+    if (ldg_u32_bytes(rec) != 2u) status |= kStBadFrameHeader;
+    if (ldg_u32_bytes(rec + 20) != (uint32_t)g.wh) status |= kStBadDepthCount;
+    if (ldg_u32_bytes(rec + 24 + g.wh) != (uint32_t)g.wh) status |= kStBadMinCount;
+    const uint32_t n64 = ldg_u32_bytes(rec + 28 + 2 * (size_t)g.wh);
+    if (tid == 0) s_flag = 0;
+    __syncthreads();
+
+    // phase 1: depth sum of every partition-warp (32 consecutive tiles of a partition)
+    const uint8_t *dp = rec + 24;
+    bool big = false;
+    for (int item = warp; item < nitems; item += 8) {
+        const int q = item >> 3, j = item & 7;
+        const PartInfo pi = part_info(g, (unsigned)q);
+        const int t = 32 * j + lane;
+        uint32_t d = 0;
+        if (t < pi.nt) d = dp[pi.tfirst + t];
+        if (d > 8) { big = true; d = 8; }
+        const uint32_t sum = __reduce_add_sync(0xffffffffu, d);
+        if (lane == 0) wp[item] = sum;
+    }
+    if (big) atomicOr(&s_flag, 1u);
+    __syncthreads();
+
+    // phase 2: exclusive scan of the nitems sums, in place, 2048 per round
+    uint32_t carry = 0;
+    for (int base = 0; base < nitems; base += 2048) {
+        uint32_t v[8], local = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int idx = base + tid * 8 + i;
+            v[i] = idx < nitems ? wp[idx] : 0u;
+            local += v[i];
+        }
+        const uint32_t incl = warp_inclusive_scan(local, lane);
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t pre = carry + incl - local, tot = 0;
+#pragma unroll
+        for (int wv = 0; wv < 8; wv++) {
+            const uint32_t t = s_warp[wv];
+            if (wv < warp) pre += t;
+            tot += t;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int idx = base + tid * 8 + i;
+            if (idx < nitems) wp[idx] = pre;
+            pre += v[i];
+        }
+        carry += tot;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        wp[nitems] = carry;
+        if (carry != n64) status |= kStBadWordCount;
+        if (s_flag) status |= kStDepthTooBig;
+        if (off + fixed + 8ull * carry > P.stream_bytes) status |= kStTruncated;
+        P.status[f] = status;
+        if (P.indices) {
+            uint64_t idx = (uint64_t)ldg_u32_bytes(rec + 4) | ((uint64_t)ldg_u32_bytes(rec + 8) << 32);
+            P.indices[f] = idx;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ main kernel
+struct DecCtl {
+    int part;                  // -1 = no more work
+    int skip;                  // frame was rejected by the scan: leave the image untouched
+    uint32_t pres, kres, mres; // residual byte offsets of payload / depth / min inside their hulls
+    uint32_t wbase[kConsumerWarps];   // word offset of each tile warp inside the partition's payload
+};
+struct DecSmem {
+    uint64_t full[kDecStages], empty[kDecStages];
+    DecCtl ctl[kDecStages];
+};
+
+template <int K>
+__device__ __forceinline__ void load_split(const uint8_t *pay, bool a4, uint32_t (&q)[16]) {
+    uint32_t x[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) x[j] = 0;
+#pragma unroll
+    for (int j = 0; j < 2 * K; j++)
+        x[j] = a4 ? reinterpret_cast<const uint32_t *>(pay)[j] : lds_u32_unaligned(pay + 4 * j);
+    split_fields<K>(x, q);
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(kDecThreads, 2) dbde_decode_kernel(const DecParams P) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    DecSmem &S = *reinterpret_cast<DecSmem *>(smem_raw);
+    uint8_t *stages = smem_raw + ((sizeof(DecSmem) + 127) & ~127);
+    const PartGeom &g = P.g;
+    uint8_t *obufs = stages + (size_t)kDecStages * kDecStageBytes;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const size_t fbytes = (size_t)g.W * g.H;
+    const int nitems = g.ppf * kConsumerWarps;
+
+    if (tid == 0) {
+        for (int s = 0; s < kDecStages; s++) {
+            mbar_init(&S.full[s], 1);
+            mbar_init(&S.empty[s], kConsumerWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == kConsumerWarps) {
+        // ============================ producer warp ============================
+        // static round-robin: nothing waits on another CTA here, so no ticket is needed and the
+        // next partition's bookkeeping loads can be issued one iteration early
+        unsigned p = blockIdx.x;
+        uint32_t nx_status = 0, nx_v = 0;
+        uint64_t nx_off = 0;
+        auto prefetch = [&](unsigned pp) {
+            if (pp < P.nparts) {
+                const PartInfo pi = part_info(g, pp);
+                nx_status = P.status[pi.f];
+                nx_off = P.frame_offsets[pi.f];
+                nx_v = lane <= kConsumerWarps ? P.wprefix[(size_t)pi.f * (nitems + 1) + pi.q * kConsumerWarps + lane] : 0u;
+            }
+        };
+        prefetch(p);
+        for (unsigned it = 0;; it++, p += gridDim.x) {
+            const int s = it % kDecStages;
+            const uint32_t ph = (it / kDecStages) & 1;
+            const uint32_t status = nx_status, v = nx_v;
+            const uint64_t off = nx_off;
+            prefetch(p + gridDim.x);
+            mbar_wait(&S.empty[s], ph ^ 1);
+            if (p >= P.nparts) {
+                if (lane == 0) {
+                    S.ctl[s].part = -1;
+                    mbar_arrive(&S.full[s]);
+                }
+                break;
+            }
+            if (status != 0) {
+                if (lane == 0) {
+                    S.ctl[s].part = (int)p;
+                    S.ctl[s].skip = 1;
+                    mbar_arrive(&S.full[s]);
+                }
+                continue;
+            }
+            const PartInfo pi = part_info(g, p);
+            const uint8_t *rec = P.stream + off;
+            const uint32_t v0 = __shfl_sync(0xffffffffu, v, 0), v8 = __shfl_sync(0xffffffffu, v, kConsumerWarps);
+            const uint32_t agg = v8 - v0;
+            uint8_t *stage = stages + (size_t)s * kDecStageBytes;
+            // lane 0: payload words, lane 1: depth bytes, lane 2: minimum bytes (16-byte hulls)
+            const uint8_t *src = nullptr;
+            uint32_t nbytes = 0;
+            uint8_t *dst = stage;
+            if (lane == 0) { src = rec + 32 + 2 * (size_t)g.wh + 8ull * v0; nbytes = 8 * agg; }
+            if (lane == 1) { src = rec + 24 + pi.tfirst; nbytes = (uint32_t)pi.nt; dst = stage + kDecPayloadBytes; }
+            if (lane == 2) { src = rec + 28 + (size_t)g.wh + pi.tfirst; nbytes = (uint32_t)pi.nt; dst = stage + kDecPayloadBytes + kDecPlaneBytes; }
+            const uintptr_t a0 = (uintptr_t)src & ~(uintptr_t)15;
+            const uintptr_t a1 = ((uintptr_t)src + nbytes + 15) & ~(uintptr_t)15;
+            const uint32_t len = nbytes ? (uint32_t)(a1 - a0) : 0u;
+            const uint32_t res = (uint32_t)((uintptr_t)src - a0);
+            if (lane < kConsumerWarps) S.ctl[s].wbase[lane] = v - v0;
+            if (lane == 0) { S.ctl[s].pres = res; S.ctl[s].part = (int)p; S.ctl[s].skip = 0; }
+            if (lane == 1) S.ctl[s].kres = res;
+            if (lane == 2) S.ctl[s].mres = res;
+            const uint32_t total = __reduce_add_sync(0xffffffffu, lane < 3 ? len : 0u);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_expect_tx(&S.full[s], total);
+            __syncwarp();
+            if (lane < 3 && len) tma_load_1d(dst, (const void *)a0, len, &S.full[s]);
+        }
+    } else {
+        // ============================ tile warps: one lane == one 8x8 tile ============================
+        int sb = 0, stx = tid;
+        if (g.nseg == 1 && g.G > 1) {
+            sb = tid / g.w;
+            stx = tid - sb * g.w;
+        }
+        unsigned ob_it = 0;                     // counts DECODED partitions: picks the output buffer
+        for (unsigned it = 0;; it++) {
+            const int s = it % kDecStages;
+            const uint32_t ph = (it / kDecStages) & 1;
+            mbar_wait(&S.full[s], ph);
+            const int part = S.ctl[s].part;
+            if (part < 0) break;
+            if (S.ctl[s].skip) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.empty[s]);
+                continue;
+            }
+            const PartInfo pi = part_info(g, (unsigned)part);
+            const uint8_t *stage = stages + (size_t)s * kDecStageBytes;
+            const bool valid = tid < pi.nt;
+            const uint32_t pres = S.ctl[s].pres;
+            int k = 0;
+            uint32_t mn = 0;
+            if (valid) {
+                k = stage[kDecPayloadBytes + S.ctl[s].kres + tid];
+                mn = stage[kDecPayloadBytes + kDecPlaneBytes + S.ctl[s].mres + tid];
+            }
+            const uint32_t incl = warp_inclusive_scan((uint32_t)k, lane);
+            const uint32_t woff = S.ctl[s].wbase[warp] + incl - (uint32_t)k;
+            const uint32_t m4 = mn * 0x01010101u;
+            uint32_t px[16];
+            if (k > 0) {
+                uint32_t q[16];
+                const uint8_t *pay = stage + pres + 8 * (size_t)woff;
+                const bool a4 = (pres & 3u) == 0;
+                switch (k) {
+                    case 1: load_split<1>(pay, a4, q); break;
+                    case 2: load_split<2>(pay, a4, q); break;
+                    case 3: load_split<3>(pay, a4, q); break;
+                    case 4: load_split<4>(pay, a4, q); break;
+                    case 5: load_split<5>(pay, a4, q); break;
+                    case 6: load_split<6>(pay, a4, q); break;
+                    case 7: load_split<7>(pay, a4, q); break;
+                    default: load_split<8>(pay, a4, q); break;
+                }
+                const uint32_t c1n = 256u - (1u << k), c2n = 65536u - (1u << (2 * k));
+                const uint32_t kmask2 = ((1u << k) - 1u) * 0x00010001u;
+#pragma unroll
+                for (int i = 0; i < 16; i++) px[i] = spread4(q[i], k, c1n, c2n, kmask2) + m4;   // +min (dbde_util.cpp:246)
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; i++) px[i] = m4;                                        // depth 0 (dbde_util.cpp:218-226)
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.empty[s]);       // payload is in registers: free the stage early
+
+            uint8_t *fptr = P.frames + (size_t)pi.f * fbytes;
+            if (FAST) {
+                uint8_t *ob = obufs + (size_t)(ob_it++ & 1) * g.stage_bytes;
+                if (valid) {
+                    uint8_t *base = ob + (size_t)(sb * 8) * g.pitch + stx * 8;
+#pragma unroll
+                    for (int r = 0; r < 8; r++)
+                        *reinterpret_cast<uint2 *>(base + (size_t)r * g.pitch) = make_uint2(px[2 * r], px[2 * r + 1]);
+                }
+                fence_proxy_async();                       // rows visible to the bulk store
+                if (warp == 0) tma_store_wait_read<0>();   // the store that last read the OTHER buffer is done
+                bar_consumers();
+                if (warp == 0) {
+                    const int nrows = pi.nbands * 8;
+                    if (g.nseg == 1 && g.pitch == g.W) {
+                        // bands are contiguous both in shared and in global memory: one store per band
+                        if (lane < pi.nbands)
+                            tma_store_1d(fptr + (size_t)(8 * (pi.y0 + lane)) * g.W, ob + (size_t)(lane * 8) * g.pitch,
+                                         (uint32_t)(8 * g.W));
+                    } else {
+                        for (int row = lane; row < nrows; row += 32)
+                            tma_store_1d(fptr + (size_t)(8 * pi.y0 + row) * g.W + 8 * pi.tx0, ob + (size_t)row * g.pitch,
+                                         (uint32_t)(8 * pi.ntx));
+                    }
+                    tma_store_commit();
+                }
+            } else if (valid) {
+                // crop the padding (dbde_util.cpp:281-289): only rows < H and columns < W are written
+                const int rows_valid = min(8, g.H - 8 * (pi.y0 + sb));
+                const int ncol = min(8, g.W - 8 * (pi.tx0 + stx));
+                uint8_t *base = fptr + (size_t)(8 * (pi.y0 + sb)) * g.W + 8 * (pi.tx0 + stx);
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    if (r < rows_valid) {
+                        uint8_t *rp = base + (size_t)r * g.W;
+                        if (ncol == 8 && (((uintptr_t)rp) & 7) == 0) {
+                            *reinterpret_cast<uint2 *>(rp) = make_uint2(px[2 * r], px[2 * r + 1]);
+                        } else {
+                            const uint64_t x = ((uint64_t)px[2 * r + 1] << 32) | px[2 * r];
+                            for (int c = 0; c < ncol; c++) rp[c] = (uint8_t)(x >> (8 * c));
+                        }
+                    }
+                }
+            }
+        }
+        if (FAST && warp == 0) tma_store_wait_all();       // shared memory must outlive the last bulk stores
+    }
+}
+
+size_t dec_smem_bytes(const PartGeom &g) {
+    return ((sizeof(DecSmem) + 127) & ~(size_t)127) + (size_t)kDecStages * kDecStageBytes + 2 * (size_t)g.stage_bytes;
+}
+
+cudaError_t launch_decode_scan(const DecParams &P, cudaStream_t stream) {
+    if (P.nframes <= 0) return cudaSuccess;
+    dbde_decode_scan_kernel<<<P.nframes, 256, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decode(const DecParams &P, bool fast, int num_sms, cudaStream_t stream) {
+    const size_t smem = dec_smem_bytes(P.g);
+    auto kern = fast ? dbde_decode_kernel<true> : dbde_decode_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kDecThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    unsigned grid = (unsigned)(num_sms * occ);
+    if (grid > P.nparts) grid = P.nparts;
+    if (grid == 0) return cudaSuccess;
+    kern<<<grid, kDecThreads, smem, stream>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace dbde

@@ -1,0 +1,280 @@
+// DBDE B200 codec -- device-side building blocks (sm_100a only).
+//
+// Everything here is written for Blackwell: bulk-TMA (cp.async.bulk -> SASS UBLKCP) staged
+// through mbarrier pipelines, VIMNMX3.U16x2 byte-min reduction, REDUX warp sums, and a
+// single-word decoupled look-back.  No tensor cores: the path has no contraction.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "dbde_b200 kernels are written for sm_100a (B200) only"
+#endif
+
+namespace dbde {
+
+// ------------------------------------------------------------------ geometry
+constexpr int kTilesPerPart = 256;              // tiles per partition == consumer threads per CTA
+constexpr int kConsumerWarps = kTilesPerPart / 32;
+constexpr int kMaxBandsPerPart = 8;             // a partition is <= 8 bands of a narrow frame ...
+constexpr int kMaxRowsPerPart = 8 * kMaxBandsPerPart;   // ... i.e. <= 64 pixel rows in one stage
+
+// How a frame is cut into partitions (the unit of the scan and of one pipeline stage).
+//   w <= 256 tiles : a partition is G consecutive 8-row bands (G*w <= 256 tiles)
+//   w  > 256 tiles : a band is cut into nseg segments of <= 256 tiles
+// Either way a partition's tiles are CONTIGUOUS in the frame's row-major tile order, so the
+// partition order is the order of the reference's running output pointer (dbde_util.cpp:155).
+struct PartGeom {
+    int W, H, w, h, wh;
+    int nseg;     // segments per band (1 when w <= 256)
+    int G;        // bands per partition when nseg == 1
+    int ppf;      // partitions per frame
+    int pitch;    // smem row pitch in bytes (multiple of 16)
+    int stage_bytes;
+};
+
+struct PartInfo {
+    int f;        // frame within the batch
+    int q;        // partition within the frame
+    int y0;       // first band
+    int nbands;   // bands in this partition
+    int tx0;      // first tile column
+    int ntx;      // tile columns
+    int nt;       // tiles = nbands * ntx
+    int tfirst;   // first tile's row-major index in the frame
+};
+
+__host__ __device__ inline PartInfo part_info(const PartGeom &g, unsigned p) {
+    PartInfo o;
+    o.f = (int)(p / (unsigned)g.ppf);
+    o.q = (int)(p - (unsigned)o.f * (unsigned)g.ppf);
+    if (g.nseg > 1) {
+        o.y0 = o.q / g.nseg;
+        int seg = o.q - o.y0 * g.nseg;
+        o.nbands = 1;
+        o.tx0 = seg * kTilesPerPart;
+        o.ntx = g.w - o.tx0 < kTilesPerPart ? g.w - o.tx0 : kTilesPerPart;
+    } else {
+        o.y0 = o.q * g.G;
+        o.nbands = g.h - o.y0 < g.G ? g.h - o.y0 : g.G;
+        o.tx0 = 0;
+        o.ntx = g.w;
+    }
+    o.nt = o.nbands * o.ntx;
+    o.tfirst = o.y0 * g.w + o.tx0;
+    return o;
+}
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// bulk TMA, global -> shared, completion on an mbarrier (SASS: UBLKCP).  16-byte aligned both sides.
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// bulk TMA, shared -> global, bulk-group completion.
+__device__ __forceinline__ void tma_store_1d(void *gdst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// order this thread's generic-proxy smem accesses against later async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(kTilesPerPart) : "memory"); }
+
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// streaming global stores (written once, never re-read by this kernel)
+__device__ __forceinline__ void st_stream_u64(void *p, uint64_t v) {
+    asm volatile("st.global.cs.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream_v2u64(void *p, uint64_t a, uint64_t b) {
+    asm volatile("st.global.cs.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void st_stream_u32(void *p, uint32_t v) {
+    asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ------------------------------------------------------------------ decoupled look-back
+// One 64-bit word per partition: [63:62] status, [61:0] value (U64 words).  Status and value
+// travel in ONE relaxed 64-bit access, so no fence is needed between them.
+constexpr uint64_t kDescInvalid = 0, kDescAggregate = 1, kDescPrefix = 2;
+constexpr uint64_t kDescValueMask = (1ull << 62) - 1;
+__device__ __forceinline__ uint64_t desc_make(uint64_t status, uint64_t value) { return (status << 62) | value; }
+
+// Called by all 32 lanes of one warp.  `p` > 0.  Returns the exclusive prefix of partition p:
+// the sum of the aggregates of partitions [0, p).  Partition 0 publishes kDescPrefix directly.
+__device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t *desc, unsigned p, int lane) {
+    uint64_t sum = 0;
+    long long look = (long long)p - 1;
+    while (true) {
+        long long idx = look - lane;
+        uint64_t d = idx >= 0 ? ld_relaxed_u64(desc + idx) : desc_make(kDescPrefix, 0);
+        unsigned st = (unsigned)(d >> 62);
+        unsigned inval = __ballot_sync(0xffffffffu, st == kDescInvalid);
+        unsigned pre = __ballot_sync(0xffffffffu, st == kDescPrefix);
+        if (pre) {
+            int j = __ffs((int)pre) - 1;                 // nearest predecessor that already knows its prefix
+            if (inval & ((1u << j) - 1u)) { __nanosleep(20); continue; }   // a nearer one is not published yet
+            uint32_t part = lane < j ? (uint32_t)(d & kDescValueMask) : 0u; // aggregates are <= 2048 each
+            sum += __reduce_add_sync(0xffffffffu, part);                    // REDUX.SUM
+            sum += __shfl_sync(0xffffffffu, d, j) & kDescValueMask;
+            return sum;
+        }
+        if (inval) { __nanosleep(20); continue; }
+        sum += __reduce_add_sync(0xffffffffu, (uint32_t)(d & kDescValueMask));
+        look -= 32;
+    }
+}
+
+// ------------------------------------------------------------------ warp scan
+__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+// ------------------------------------------------------------------ per-tile arithmetic (one lane == one 8x8 tile)
+// px[2r], px[2r+1] = the 8 pixels of tile row r, little-endian.
+
+// exact minimum of the 64 bytes: u16x2 min over {w, w<<8} puts every byte in a high-byte slot
+// (VIMNMX3.U16x2; the byte-wise __vminu4 is a 7-instruction emulation on sm_100a).
+__device__ __forceinline__ uint32_t tile_min(const uint32_t (&px)[16]) {
+    uint32_t a = 0xffffffffu;
+#pragma unroll
+    for (int i = 0; i < 16; i++) a = __vimin3_u16x2(a, px[i], px[i] << 8);
+    uint32_t hi = a >> 24, lo = (a >> 8) & 0xffu;
+    return hi < lo ? hi : lo;
+}
+
+// px -= min (no byte borrows: every byte >= min); returns depth = bits(max - min) via the OR of
+// the differences (the top set bit of an OR is the top set bit of the maximum).  dbde_util.cpp:48-68.
+__device__ __forceinline__ int tile_subtract_depth(uint32_t (&px)[16], uint32_t mn) {
+    const uint32_t m4 = mn * 0x01010101u;
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        px[i] -= m4;
+        o |= px[i];
+    }
+    o |= o >> 16;
+    o |= o >> 8;
+    return 32 - __clz((int)(o & 0xffu));
+}
+
+// 4 bytes of <= k bits each  ->  one 4k-bit field.  Two multiply-adds per word, valid for k = 1..8:
+//   pairs : w = e + 256*o        ->  p = e + 2^k*o      = w + o*(2^k - 256)
+//   quads : p = l + 65536*h      ->  q = l + 2^(2k)*h   = p + h*(2^2k - 65536)
+// (the role pmaddubsw/pmaddwd play at dbde_util.cpp:70-80)
+__device__ __forceinline__ uint32_t squeeze4(uint32_t d, uint32_t c1, uint32_t c2) {
+    uint32_t odd = __byte_perm(d, 0u, 0x4341);       // {b1, 0, b3, 0}
+    uint32_t p = d + odd * c1;
+    return p + (p >> 16) * c2;
+}
+// inverse: one 4k-bit field -> 4 bytes
+//   q = l + 2^2k*h -> p = q + h*(65536 - 2^2k);   p = e + 2^k*o (per u16) -> w = p + o*(256 - 2^k)
+__device__ __forceinline__ uint32_t spread4(uint32_t q, int k, uint32_t c1n, uint32_t c2n, uint32_t kmask2) {
+    uint32_t p = q + (q >> (2 * k)) * c2n;
+    uint32_t odd = (p >> k) & kmask2;                // kmask2 = ((1<<k)-1) * 0x00010001
+    return p + odd * c1n;
+}
+
+// Concatenate sixteen 4K-bit fields LSB-first into K little-endian U64 words.  Everything is
+// compile-time after unrolling: constant shifts, unconditional stores.
+template <int K, typename Store>
+__device__ __forceinline__ void concat_fields(const uint32_t (&q)[16], Store &&store) {
+    uint64_t acc = 0;
+    int b = 0, n = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        uint64_t v = q[i];
+        acc |= v << b;
+        if (b + 4 * K >= 64) {
+            store(n, acc);
+            n++;
+            acc = (b + 4 * K > 64) ? (v >> (64 - b)) : 0ull;
+            b = b + 4 * K - 64;
+        } else {
+            b += 4 * K;
+        }
+    }
+}
+// inverse of concat_fields: K U64 words (as 2K u32) -> sixteen 4K-bit fields
+template <int K>
+__device__ __forceinline__ void split_fields(const uint32_t (&x)[16], uint32_t (&q)[16]) {
+    constexpr uint32_t fmask = (K == 8) ? 0xffffffffu : ((1u << (4 * K)) - 1u);
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const int bit = 4 * K * i;
+        const int j = bit >> 5, sh = bit & 31;
+        uint32_t v = x[j] >> sh;
+        if (sh + 4 * K > 32) v |= x[j + 1] << (32 - sh);
+        q[i] = v & fmask;
+    }
+}
+
+// staging swizzle at U64 granularity: spreads equal-depth lanes (stride K words) over the banks
+__device__ __forceinline__ uint32_t swz(uint32_t a) { return a ^ ((a >> 4) & 15u); }
+
+// unaligned-safe shared loads for the generic (odd width / odd offset) paths
+__device__ __forceinline__ uint32_t lds_u32_unaligned(const uint8_t *p) {
+    uint32_t a = smem_u32(p);
+    const uint32_t *q = (const uint32_t *)(p - (a & 3u));
+    uint32_t sh = (a & 3u) * 8u;
+    uint32_t x0 = q[0];
+    if (sh == 0) return x0;
+    return __funnelshift_r(x0, q[1], sh);
+}
+__device__ __forceinline__ uint2 lds_u64_unaligned(const uint8_t *p) {
+    uint32_t a = smem_u32(p);
+    const uint32_t *q = (const uint32_t *)(p - (a & 3u));
+    uint32_t sh = (a & 3u) * 8u;
+    uint32_t x0 = q[0], x1 = q[1];
+    if (sh == 0) return make_uint2(x0, x1);
+    uint32_t x2 = q[2];
+    return make_uint2(__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh));
+}
+#endif  // __CUDACC__
+
+}  // namespace dbde

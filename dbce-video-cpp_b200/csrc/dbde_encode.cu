@@ -1,0 +1,318 @@
+// DBDE B200 encoder: raw U8 frames in HBM -> DBDE frame records laid back to back in HBM,
+// byte-identical to what dbde_pack_frame (dbde_util.cpp:190-196) writes frame after frame.
+//
+// One persistent kernel, one pass over the pixels:
+//   warp 8  (producer) : claims partitions from an atomic ticket and bulk-TMAs their pixel rows
+//                        into a ring of shared-memory stages (mbarrier full/empty pipeline)
+//   warps 0-7 (tiles)  : one lane per 8x8 tile -- min, depth = bits(max-min), bit packing; the
+//                        payload words are staged in the (now dead) pixel stage and copied out
+//                        with coalesced stores
+//   warp 9  (scan)     : publishes the partition's depth sum, resolves its exclusive prefix with
+//                        a single-pass decoupled look-back, and hands the output address to the
+//                        tile warps; writes the frame's fixed fields (header, lengths, n64)
+// The look-back chain runs over the whole batch, so every frame record lands at its final
+// offset (frame f starts at sum of the sizes of frames < f) and the device buffer is the file
+// image minus the 28-byte video header.
+#include "dbde_device.cuh"
+#include "dbde_kernels.h"
+
+namespace dbde {
+
+constexpr int kEncStages = 3;
+constexpr int kEncThreads = kTilesPerPart + 64;
+
+struct EncCtl {                 // per-stage control block, written by the producer warp
+    int part;                   // partition id, -1 = no more work
+    uint16_t rowoff[kMaxRowsPerPart];   // byte offset of each row's first pixel inside its smem row
+};
+struct EncBase {                // per-stage, written by the scan warp
+    uint8_t *frame;             // where this frame's record starts
+    uint8_t *payload;           // where this partition's first U64 word goes
+};
+
+struct EncSmem {
+    uint64_t full[kEncStages], empty[kEncStages], aggbar[kEncStages], basebar[kEncStages];
+    EncCtl ctl[kEncStages];
+    EncBase base[kEncStages];
+    uint32_t warptot[kEncStages][kConsumerWarps];
+};
+
+template <bool FAST>
+__global__ void __launch_bounds__(kEncThreads, 2) dbde_encode_kernel(const EncParams P) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    EncSmem &S = *reinterpret_cast<EncSmem *>(smem_raw);
+    uint8_t *stages = smem_raw + ((sizeof(EncSmem) + 127) & ~127);
+    const PartGeom &g = P.g;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < kEncStages; s++) {
+            mbar_init(&S.full[s], 1);
+            mbar_init(&S.empty[s], kConsumerWarps);
+            mbar_init(&S.aggbar[s], kConsumerWarps);
+            mbar_init(&S.basebar[s], 1);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == kConsumerWarps) {
+        // ============================ producer warp ============================
+        const size_t fbytes = (size_t)g.W * g.H;
+        for (unsigned it = 0;; it++) {
+            const int s = it % kEncStages;
+            const uint32_t ph = (it / kEncStages) & 1;
+            mbar_wait(&S.empty[s], ph ^ 1);
+            unsigned p = 0;
+            if (lane == 0) p = atomicAdd(P.ticket, 1u);
+            p = __shfl_sync(0xffffffffu, p, 0);
+            if (p >= P.nparts) {
+                if (lane == 0) {
+                    S.ctl[s].part = -1;
+                    mbar_arrive(&S.full[s]);
+                }
+                break;
+            }
+            const PartInfo pi = part_info(g, p);
+            const uint8_t *fptr = P.frames + (size_t)pi.f * fbytes;
+            uint8_t *stage = stages + (size_t)s * g.stage_bytes;
+            const int nrows = pi.nbands * 8;
+            const int rowbytes = min(8 * pi.ntx, g.W - 8 * pi.tx0);
+            // each lane owns rows lane, lane+32
+            uint32_t mybytes = 0;
+            const uint8_t *src[2];
+            uint32_t len[2];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int row = lane + 32 * j;
+                len[j] = 0;
+                src[j] = nullptr;
+                if (row < nrows) {
+                    const int y = 8 * pi.y0 + row;
+                    if (y < g.H) {
+                        const uint8_t *a = fptr + (size_t)y * g.W + 8 * pi.tx0;
+                        const uintptr_t a0 = (uintptr_t)a & ~(uintptr_t)15;
+                        const uintptr_t a1 = ((uintptr_t)a + rowbytes + 15) & ~(uintptr_t)15;
+                        src[j] = (const uint8_t *)a0;
+                        len[j] = (uint32_t)(a1 - a0);
+                        S.ctl[s].rowoff[row] = (uint16_t)((uintptr_t)a - a0);
+                    }
+                }
+                mybytes += len[j];
+            }
+            const uint32_t total = __reduce_add_sync(0xffffffffu, mybytes);
+            __syncwarp();               // every lane's rowoff[] store precedes the release below
+            if (lane == 0) {
+                S.ctl[s].part = (int)p;
+                mbar_arrive_expect_tx(&S.full[s], total);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+                if (len[j]) tma_load_1d(stage + (size_t)(lane + 32 * j) * g.pitch, src[j], len[j], &S.full[s]);
+        }
+    } else if (warp == kConsumerWarps + 1) {
+        // ============================ scan warp ============================
+        int cached_f = -1;
+        uint64_t cached_start = 0;
+        for (unsigned it = 0;; it++) {
+            const int s = it % kEncStages;
+            const uint32_t ph = (it / kEncStages) & 1;
+            mbar_wait(&S.full[s], ph);
+            const int part = S.ctl[s].part;
+            if (part < 0) break;
+            const unsigned p = (unsigned)part;
+            const PartInfo pi = part_info(g, p);
+            mbar_wait(&S.aggbar[s], ph);
+            uint32_t wt = lane < kConsumerWarps ? S.warptot[s][lane] : 0u;
+            const uint64_t agg = __reduce_add_sync(0xffffffffu, wt);
+            uint64_t excl = 0;
+            if (p == 0) {
+                if (lane == 0) st_relaxed_u64(P.desc, desc_make(kDescPrefix, agg));
+            } else {
+                if (lane == 0) st_relaxed_u64(P.desc + p, desc_make(kDescAggregate, agg));
+                excl = lookback_exclusive(P.desc, p, lane);
+                if (lane == 0) st_relaxed_u64(P.desc + p, desc_make(kDescPrefix, excl + agg));
+            }
+            // words written by all frames before this one
+            uint64_t fstart;
+            if (pi.q == 0) {
+                fstart = excl;
+                if (lane == 0) st_relaxed_u64(P.fstart + pi.f, (1ull << 63) | excl);
+            } else if (pi.f == cached_f) {
+                fstart = cached_start;
+            } else {
+                uint64_t v;
+                do { v = ld_relaxed_u64(P.fstart + pi.f); } while (!(v >> 63));
+                fstart = v & ~(1ull << 63);
+            }
+            cached_f = pi.f;
+            cached_start = fstart;
+            const size_t fixed = 32 + 2 * (size_t)g.wh;     // frame header + lengths + planes
+            uint8_t *frame = P.out + (size_t)pi.f * fixed + 8 * fstart;
+            if (lane == 0) {
+                S.base[s].frame = frame;
+                S.base[s].payload = frame + fixed + 8 * (excl - fstart);
+                mbar_arrive(&S.basebar[s]);
+            }
+            if (pi.q == g.ppf - 1) {
+                // last partition of the frame: the fixed fields (dbde_util.cpp:141-146,182-188,191)
+                const uint32_t n64 = (uint32_t)(excl + agg - fstart);
+                const uint64_t index = P.first_index + (uint64_t)pi.f;
+                uint32_t b;      // lane i writes one byte of {I32 2 | U64 index | F64 0.0 | I32 wh} {I32 wh} {I32 n64}
+                uint8_t *dst;
+                if (lane < 4) { b = (2u >> (8 * lane)) & 0xff; dst = frame + lane; }
+                else if (lane < 12) { b = (uint32_t)(index >> (8 * (lane - 4))) & 0xff; dst = frame + lane; }
+                else if (lane < 20) { b = 0; dst = frame + lane; }
+                else if (lane < 24) { b = ((uint32_t)g.wh >> (8 * (lane - 20))) & 0xff; dst = frame + lane; }
+                else if (lane < 28) { b = ((uint32_t)g.wh >> (8 * (lane - 24))) & 0xff; dst = frame + 24 + g.wh + (lane - 24); }
+                else { b = (n64 >> (8 * (lane - 28))) & 0xff; dst = frame + 28 + 2 * (size_t)g.wh + (lane - 28); }
+                *dst = (uint8_t)b;
+                if (lane == 0) {
+                    const uint64_t off = (uint64_t)(frame - P.out);
+                    P.frame_offsets[pi.f] = off;
+                    if (pi.f == P.nframes - 1) P.frame_offsets[P.nframes] = off + fixed + 8ull * n64;
+                }
+            }
+        }
+    } else {
+        // ============================ tile warps: one lane == one 8x8 tile ============================
+        int sb = 0, stx = tid;                  // slot -> (band within partition, tile column)
+        if (g.nseg == 1 && g.G > 1) {
+            sb = tid / g.w;
+            stx = tid - sb * g.w;
+        }
+        for (unsigned it = 0;; it++) {
+            const int s = it % kEncStages;
+            const uint32_t ph = (it / kEncStages) & 1;
+            mbar_wait(&S.full[s], ph);
+            const int part = S.ctl[s].part;
+            if (part < 0) break;
+            const PartInfo pi = part_info(g, (unsigned)part);
+            uint8_t *stage = stages + (size_t)s * g.stage_bytes;
+            const bool valid = tid < pi.nt;
+            const int asb = valid ? sb : 0, astx = valid ? stx : 0;   // idle lanes read (and discard) tile 0
+
+            // ---- stage (1)->registers: 8 rows x 8 bytes
+            uint32_t px[16];
+            if (FAST) {
+                const uint8_t *base = stage + (size_t)(asb * 8) * g.pitch + astx * 8;
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    uint2 v = *reinterpret_cast<const uint2 *>(base + (size_t)r * g.pitch);
+                    px[2 * r] = v.x;
+                    px[2 * r + 1] = v.y;
+                }
+            } else {
+                // clamp-to-edge padding (dbde_util.cpp:105-135): rows past H repeat the last valid
+                // row, columns past W repeat the last valid pixel of the row
+                const int rows_valid = min(8, g.H - 8 * (pi.y0 + sb));
+                const int ncol = min(8, g.W - 8 * (pi.tx0 + stx));
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    uint2 v = make_uint2(0u, 0u);
+                    if (valid) {
+                        const int row = sb * 8 + min(r, rows_valid - 1);
+                        v = lds_u64_unaligned(stage + (size_t)row * g.pitch + S.ctl[s].rowoff[row] + stx * 8);
+                        if (ncol < 8) {
+                            uint64_t x = ((uint64_t)v.y << 32) | v.x;
+                            const uint64_t last = (x >> (8 * (ncol - 1))) & 0xffull;
+                            const uint64_t keep = (1ull << (8 * ncol)) - 1ull;
+                            x = (x & keep) | ((last * 0x0101010101010101ull) & ~keep);
+                            v = make_uint2((uint32_t)x, (uint32_t)(x >> 32));
+                        }
+                    }
+                    px[2 * r] = v.x;
+                    px[2 * r + 1] = v.y;
+                }
+            }
+            // ---- stage (2): min, depth
+            uint32_t mn = tile_min(px);
+            int k = tile_subtract_depth(px, mn);
+            if (!valid) { k = 0; mn = 0; }
+            // ---- stage (3a): depth sums -> scan warp
+            const uint32_t incl = warp_inclusive_scan((uint32_t)k, lane);
+            if (lane == 31) {
+                S.warptot[s][warp] = incl;
+                mbar_arrive(&S.aggbar[s]);
+            }
+            bar_consumers();            // every tile is in registers: the stage may be overwritten
+            uint32_t off = incl - (uint32_t)k;
+            uint32_t total = 0;
+#pragma unroll
+            for (int wv = 0; wv < kConsumerWarps; wv++) {
+                const uint32_t t = S.warptot[s][wv];
+                if (wv < warp) off += t;
+                total += t;
+            }
+            // ---- stage (4): pack (p - min) into k U64 words, staged (swizzled) in the dead pixel stage
+            if (k > 0) {
+                const uint32_t c1 = (1u << k) - 256u, c2 = (1u << (2 * k)) - 65536u;
+                uint32_t q[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) q[i] = squeeze4(px[i], c1, c2);
+                uint64_t *st64 = reinterpret_cast<uint64_t *>(stage);
+                auto store = [&](int n, uint64_t v) { st64[swz(off + (uint32_t)n)] = v; };
+                switch (k) {
+                    case 1: concat_fields<1>(q, store); break;
+                    case 2: concat_fields<2>(q, store); break;
+                    case 3: concat_fields<3>(q, store); break;
+                    case 4: concat_fields<4>(q, store); break;
+                    case 5: concat_fields<5>(q, store); break;
+                    case 6: concat_fields<6>(q, store); break;
+                    case 7: concat_fields<7>(q, store); break;
+                    default: concat_fields<8>(q, store); break;
+                }
+            }
+            bar_consumers();            // payload staged
+            mbar_wait(&S.basebar[s], ph);
+            uint8_t *frame = S.base[s].frame;
+            uint8_t *payload = S.base[s].payload;
+            // ---- depth and minimum planes (dbde_util.cpp:156-157)
+            if (valid) {
+                frame[24 + pi.tfirst + tid] = (uint8_t)k;
+                frame[28 + (size_t)g.wh + pi.tfirst + tid] = (uint8_t)mn;
+            }
+            // ---- coalesced copy-out of the partition's `total` words
+            {
+                const uint64_t *st64 = reinterpret_cast<const uint64_t *>(stage);
+                const uintptr_t ga = (uintptr_t)payload;
+                if ((ga & 7) == 0) {
+                    for (uint32_t i = tid; i < total; i += kTilesPerPart) st_stream_u64(payload + 8 * (size_t)i, st64[swz(i)]);
+                } else if ((ga & 3) == 0) {
+                    const uint32_t *st32 = reinterpret_cast<const uint32_t *>(stage);
+                    for (uint32_t i = tid; i < 2 * total; i += kTilesPerPart)
+                        st_stream_u32(payload + 4 * (size_t)i, st32[2 * swz(i >> 1) + (i & 1)]);
+                } else {
+                    for (uint32_t i = tid; i < 8 * total; i += kTilesPerPart)
+                        payload[i] = stage[8 * swz(i >> 3) + (i & 7)];
+                }
+            }
+            fence_proxy_async();        // my generic accesses to the stage precede the next TMA fill
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.empty[s]);
+        }
+    }
+}
+
+size_t enc_smem_bytes(const PartGeom &g) {
+    return ((sizeof(EncSmem) + 127) & ~(size_t)127) + (size_t)kEncStages * g.stage_bytes;
+}
+
+cudaError_t launch_encode(const EncParams &P, bool fast, int num_sms, cudaStream_t stream) {
+    const size_t smem = enc_smem_bytes(P.g);
+    auto kern = fast ? dbde_encode_kernel<true> : dbde_encode_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kEncThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    unsigned grid = (unsigned)(num_sms * occ);
+    if (grid > P.nparts) grid = P.nparts;
+    if (grid == 0) return cudaSuccess;
+    kern<<<grid, kEncThreads, smem, stream>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace dbde

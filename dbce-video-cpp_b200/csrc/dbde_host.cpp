@@ -1,0 +1,317 @@
+// Host-side mirror of the reference's C++ interface (include/dbde_util.h).
+//
+// The frame entry points forward to the extern "C" layer (GPU); headers are marshalled here
+// (no arithmetic to accelerate); the tile-level functions are expressed as
+// one-tile frames so they run the very same device code; the file walker decodes whole
+// buffers of frames per GPU batch and hands them out one per call.
+#pragma GCC visibility push(default)      // the sixteen reference entry points are the library's C++ surface
+#include "../../include/dbde_util.h"
+#pragma GCC visibility pop
+#include "../../include/dbde_b200.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+
+// One lazily created context per calling thread: keeps the reference's "re-entrant, callable
+// from several threads on disjoint buffers" property without a global lock.
+struct ThreadCtx {
+    dbde_b200_ctx *ctx = nullptr;
+    ~ThreadCtx() {
+        if (ctx) dbde_b200_destroy(ctx);
+    }
+};
+
+dbde_b200_ctx *ctx() {
+    static thread_local ThreadCtx t;
+    if (!t.ctx) {
+        const char *dev = getenv("DBDE_B200_DEVICE");
+        int rc = dbde_b200_create(dev ? atoi(dev) : 0, &t.ctx);
+        if (rc != 0 || !t.ctx) {
+            // there is no CPU fallback: the drop-in signatures cannot report this, so stop loudly
+            fprintf(stderr, "dbde_b200: cannot create a GPU context (%d): %s\n", rc, dbde_b200_last_error());
+            abort();
+        }
+    }
+    return t.ctx;
+}
+
+void die(const char *what, int rc) {
+    fprintf(stderr, "dbde_b200: %s failed (%d): %s\n", what, rc, dbde_b200_last_error());
+    abort();
+}
+
+inline void put32(uint8_t *p, uint32_t v) { memcpy(p, &v, 4); }
+inline void put64(uint8_t *p, uint64_t v) { memcpy(p, &v, 8); }
+inline uint32_t get32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+inline uint64_t get64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
+
+}  // namespace
+
+// ---------------------------------------------------------------- headers (host only)
+// reference dbde_util.cpp:182-188
+size_t dbde_pack_frame_header(frame_header fh, uint8_t *target) {
+    const double e = (double)fh.elapsed_ns;
+    put32(target, fh.u64s);
+    put64(target + 4, fh.index);
+    memcpy(target + 12, &e, 8);
+    return 20;
+}
+// reference dbde_util.cpp:198-209 (default build: frame_hz is a double)
+size_t dbde_pack_video_header(video_header vh, uint8_t *target) {
+    put32(target, vh.u64s);
+    put64(target + 4, vh.height);
+    put64(target + 12, vh.width);
+    memcpy(target + 20, &vh.frame_hz, 8);
+    return 28;
+}
+// reference dbde_util.cpp:330-337
+frame_header dbde_unpack_frame_header(uint8_t **packed) {
+    const uint8_t *p = *packed;
+    frame_header fh;
+    double e;
+    fh.u64s = get32(p);
+    fh.index = get64(p + 4);
+    memcpy(&e, p + 12, 8);
+    fh.elapsed_ns = (uint64_t)e;
+    *packed += 20;
+    if (fh.u64s != 2) fh.u64s = (uint32_t)-1;
+    return fh;
+}
+// reference dbde_util.cpp:347-359
+video_header dbde_unpack_video_header(uint8_t **packed) {
+    const uint8_t *p = *packed;
+    video_header vh;
+    vh.u64s = get32(p);
+    vh.height = get64(p + 4);
+    vh.width = get64(p + 12);
+    memcpy(&vh.frame_hz, p + 20, 8);
+    *packed += 28;
+    if (vh.u64s != 3) vh.u64s = (uint32_t)-1;
+    return vh;
+}
+
+// ---------------------------------------------------------------- frames (GPU)
+// reference dbde_util.cpp:190-196
+size_t dbde_pack_frame(uint64_t index, uint8_t *image, int W, int H, uint8_t *target) {
+    uint64_t offs[2];
+    int rc = dbde_b200_encode_host(ctx(), image, W, H, index, 1, target, dbde_b200_frame_record_bound(W, H), offs);
+    if (rc) die("dbde_pack_frame", rc);
+    return (size_t)offs[1];
+}
+// reference dbde_util.cpp:137-180: the frame record minus its 20-byte header
+size_t dbde_pack_image(uint8_t *image, int W, int H, uint8_t *target) {
+    std::vector<uint8_t> rec(dbde_b200_frame_record_bound(W, H));
+    const size_t n = dbde_pack_frame(0, image, W, H, rec.data());
+    memcpy(target, rec.data() + 20, n - 20);
+    return n - 20;
+}
+// reference dbde_util.cpp:339-345
+frame_header dbde_unpack_frame(uint8_t **packed, int W, int H, uint8_t *image) {
+    uint8_t *rec = *packed;
+    frame_header fh = dbde_unpack_frame_header(packed);        // always advances 20 bytes
+    // the reference has no length argument: bound the record by what its own fields claim
+    const size_t wh = (size_t)((W + 7) / 8) * ((H + 7) / 8);
+    const size_t n64 = get32(rec + 28 + 2 * wh);
+    if (n64 > 8 * wh) {                                        // cannot equal sum(depth <= 8): reject without
+        fh.u64s = (uint32_t)-1;                                // reading past what a legal record may occupy
+        return fh;
+    }
+    const size_t bytes = 32 + 2 * wh + 8 * n64;
+    uint8_t hdr_ok[4];
+    put32(hdr_ok, 2);                                          // image validity is independent of the tag (:341)
+    std::vector<uint8_t> tmp;
+    const uint8_t *src = rec;
+    if (get32(rec) != 2) {
+        tmp.assign(rec, rec + (bytes < 32 + 2 * wh ? 32 + 2 * wh : bytes));
+        memcpy(tmp.data(), hdr_ok, 4);
+        src = tmp.data();
+    }
+    const uint64_t off0 = 0;
+    uint32_t status = 0;
+    int rc = dbde_b200_decode_host(ctx(), src, bytes, &off0, W, H, 1, image, &status, nullptr);
+    if (rc) die("dbde_unpack_frame", rc);
+    if (status != 0) fh.u64s = (uint32_t)-1;                   // pointer stays just after the header (:342)
+    else *packed = rec + bytes;
+    return fh;
+}
+// reference dbde_util.cpp:291-328: returns bytes consumed, 0 on a malformed block
+size_t dbde_unpack_image(uint8_t *packed, int W, int H, uint8_t *image) {
+    const size_t wh = (size_t)((W + 7) / 8) * ((H + 7) / 8);
+    const size_t n64 = get32(packed + 8 + 2 * wh);
+    if (n64 > 8 * wh) return 0;
+    const size_t body = 12 + 2 * wh + 8 * n64;
+    std::vector<uint8_t> rec(20 + body);
+    frame_header fh = {2, 0, 0};
+    dbde_pack_frame_header(fh, rec.data());
+    memcpy(rec.data() + 20, packed, body);
+    uint8_t *p = rec.data();
+    frame_header out = dbde_unpack_frame(&p, W, H, image);
+    return out.u64s == 2 ? body : 0;
+}
+
+// ---------------------------------------------------------------- single tiles (GPU, as 1-tile frames)
+// reference dbde_util.cpp:105-135: an (downmargin x rightmargin) corner IS a W=rightmargin,
+// H=downmargin frame; the device clamp-pads it exactly as dbde_pack_8x8_partial does
+uint32_t dbde_pack_8x8_partial(uint8_t *image, int stride, int rightmargin, int downmargin, uint8_t *target) {
+    uint8_t px[64], rec[32 + 66];
+    for (int y = 0; y < downmargin; y++) memcpy(px + y * rightmargin, image + (size_t)y * stride, rightmargin);
+    const size_t n = dbde_pack_frame(0, px, rightmargin, downmargin, rec);
+    const uint32_t depth = rec[24], mn = rec[29];
+    memcpy(target, rec + 34, n - 34);                          // exactly 8*depth bytes
+    return (depth << 8) | mn;
+}
+// reference dbde_util.cpp:22-103
+uint32_t dbde_pack_8x8(uint8_t *image, int stride, uint8_t *target) {
+    return dbde_pack_8x8_partial(image, stride, 8, 8, target);
+}
+// reference dbde_util.cpp:216-279 (depth >= 8 reads 64 raw bytes, :229)
+void dbde_unpack_8x8(uint8_t depth, uint8_t minval, uint8_t *packed, size_t stride, uint8_t *image) {
+    const uint32_t k = depth > 8 ? 8 : depth;
+    uint8_t rec[34 + 64], px[64];
+    frame_header fh = {2, 0, 0};
+    dbde_pack_frame_header(fh, rec);
+    put32(rec + 20, 1);
+    rec[24] = (uint8_t)k;
+    put32(rec + 25, 1);
+    rec[29] = minval;
+    put32(rec + 30, k);
+    memcpy(rec + 34, packed, 8 * k);
+    uint8_t *p = rec;
+    dbde_unpack_frame(&p, 8, 8, px);
+    for (int y = 0; y < 8; y++) memcpy(image + y * stride, px + 8 * y, 8);
+}
+// reference dbde_util.cpp:281-289
+void dbde_unpack_8x8_partial(uint8_t depth, uint8_t minval, uint8_t *packed, size_t stride, int rightmargin,
+                             int downmargin, uint8_t *image) {
+    uint8_t img[64];
+    dbde_unpack_8x8(depth, minval, packed, 8, img);
+    for (int y = 0; y < downmargin; y++) memcpy(image + stride * y, img + 8 * y, rightmargin);
+}
+
+// ---------------------------------------------------------------- file walker
+// Same interface and field meanings as the reference (dbde_util.cpp:362-426) but: the buffer is
+// sized for the true worst-case record (32 + 66*wh, not npix + npix/8 + 32, which under-sizes
+// small odd frames), it is freed in dbde_end_file_walk, and frames are decoded on the GPU in
+// batches of `frames_buffered` and handed out one per call.
+namespace {
+struct WalkerSide {
+    std::vector<uint8_t> frames;        // decoded batch
+    std::vector<frame_header> hdrs;
+    size_t next = 0, have = 0;
+    bool eof = false;
+    int batch = 1;
+};
+std::mutex g_wmx;
+std::unordered_map<uint8_t *, WalkerSide *> g_wside;      // keyed by walker->buffer
+
+WalkerSide *side_of(const dbde_file_walker *w) {
+    std::lock_guard<std::mutex> lk(g_wmx);
+    auto it = g_wside.find(w->buffer);
+    return it == g_wside.end() ? nullptr : it->second;
+}
+
+// keep [i, n) topped up from the file (reference dbde_advance_file_buffer, :394-406)
+bool refill(dbde_file_walker *w) {
+    if (w->i > 0) {
+        if (w->i < w->n) memmove(w->buffer, w->buffer + w->i, w->n - w->i);
+        w->n -= w->i;
+        w->i = 0;
+    }
+    if (!feof(w->fptr)) {
+        w->n += fread(w->buffer + w->n, 1, w->N - w->n, w->fptr);
+        if (ferror(w->fptr)) return false;
+    }
+    return true;
+}
+}  // namespace
+
+dbde_file_walker dbde_start_file_walk(const char *name, int frames_buffered, video_header *vh) {
+    if (frames_buffered < 1) frames_buffered = 2;
+    dbde_file_walker w = {NULL, 0, 0, 0, 0, 1, 1, NULL};
+    FILE *f = fopen(name, "rb");
+    if (!f) return w;
+    uint8_t head[28];
+    if (fread(head, 1, 28, f) != 28) { fclose(f); return w; }
+    uint8_t *hp = head;
+    *vh = dbde_unpack_video_header(&hp);
+    // same sanity limits as the reference (:374-378)
+    if (vh->u64s != 3 || vh->height == 0 || vh->width == 0 || vh->height > 0x37FFFFFF || vh->width > 0x37FFFFFF ||
+        vh->height * vh->width > 0x37FFFFFF) {
+        fclose(f);
+        return w;
+    }
+    const size_t bound = dbde_b200_frame_record_bound((int)vh->width, (int)vh->height);
+    const size_t N = bound * (size_t)frames_buffered + 64;
+    if (N >= 0x7FFFFFFF) { fclose(f); return w; }
+    w.buffer = (uint8_t *)malloc(N);
+    if (!w.buffer) { fclose(f); return w; }
+    w.fptr = f;
+    w.N = N;
+    w.width = (int32_t)vh->width;
+    w.height = (int32_t)vh->height;
+    w.n = fread(w.buffer, 1, N, f);
+    if (ferror(f)) { fclose(f); free(w.buffer); w.buffer = NULL; w.fptr = NULL; return w; }
+    WalkerSide *s = new WalkerSide();
+    s->batch = frames_buffered;
+    s->frames.resize((size_t)frames_buffered * w.width * w.height);
+    s->hdrs.resize(frames_buffered);
+    std::lock_guard<std::mutex> lk(g_wmx);
+    g_wside[w.buffer] = s;
+    return w;
+}
+
+bool dbde_walk_a_file(dbde_file_walker *w, frame_header *fh, uint8_t *image) {
+    if (!w || !w->fptr) return false;
+    WalkerSide *s = side_of(w);
+    if (!s) return false;
+    const size_t px = (size_t)w->width * w->height;
+    if (s->next == s->have) {
+        // decode the next batch of whole records that are in (or can be read into) the buffer
+        if (!refill(w)) { dbde_end_file_walk(w); return false; }
+        std::vector<uint64_t> offs(s->batch + 1);
+        const long n = dbde_b200_index_stream(w->buffer + w->i, w->n - w->i, w->width, w->height, offs.data(), s->batch);
+        if (n <= 0) return false;                          // end of file (or a torn last record)
+        std::vector<uint32_t> status(n);
+        std::vector<uint64_t> index(n);
+        int rc = dbde_b200_decode_host(ctx(), w->buffer + w->i, (size_t)offs[n], offs.data(), w->width, w->height,
+                                       (int)n, s->frames.data(), status.data(), index.data());
+        if (rc) die("dbde_walk_a_file", rc);
+        s->have = 0;
+        for (long k = 0; k < n; k++) {
+            uint8_t *p = w->buffer + w->i + offs[k];
+            s->hdrs[k] = dbde_unpack_frame_header(&p);
+            if (status[k] != 0) s->hdrs[k].u64s = (uint32_t)-1;
+            s->have++;
+            if (status[k] != 0) break;                     // stop handing out frames at the first bad one
+        }
+        s->next = 0;
+        w->i += (size_t)offs[n];
+    }
+    *fh = s->hdrs[s->next];
+    if (fh->u64s != 2) { dbde_end_file_walk(w); return false; }   // reference :416
+    memcpy(image, s->frames.data() + px * s->next, px);
+    s->next++;
+    w->frames++;
+    return true;
+}
+
+void dbde_end_file_walk(dbde_file_walker *w) {
+    if (!w) return;
+    if (w->fptr) fclose(w->fptr);
+    w->fptr = NULL;
+    if (w->buffer) {
+        {
+            std::lock_guard<std::mutex> lk(g_wmx);
+            auto it = g_wside.find(w->buffer);
+            if (it != g_wside.end()) { delete it->second; g_wside.erase(it); }
+        }
+        free(w->buffer);
+        w->buffer = NULL;
+    }
+}

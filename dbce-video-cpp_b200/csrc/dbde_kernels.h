@@ -1,0 +1,49 @@
+// Internal interface between the C ABI (dbde_capi.cu) and the kernels.
+#pragma once
+#include "dbde_device.cuh"
+
+namespace dbde {
+
+struct EncParams {
+    PartGeom g;
+    const uint8_t *frames;      // nframes * W * H, tightly packed, device
+    uint8_t *out;               // where frame record 0 starts, device
+    uint64_t *frame_offsets;    // nframes + 1 entries, device
+    uint64_t *desc;             // nparts look-back descriptors, zeroed
+    uint64_t *fstart;           // nframes frame-start slots, zeroed
+    unsigned int *ticket;       // zeroed
+    uint64_t first_index;
+    int nframes;
+    unsigned nparts;
+};
+
+struct DecParams {
+    PartGeom g;
+    const uint8_t *stream;      // frame records, device
+    uint64_t stream_bytes;
+    const uint64_t *frame_offsets;   // nframes entries (record starts), device
+    uint8_t *frames;            // nframes * W * H out, device
+    uint32_t *status;           // nframes
+    uint64_t *indices;          // nframes or null
+    uint32_t *wprefix;          // nframes * (ppf*8 + 1) exclusive word prefixes per partition-warp
+    int nframes;
+    unsigned nparts;
+};
+
+// status bits reported by the decoder (0 = frame decoded)
+enum : uint32_t {
+    kStBadFrameHeader = 1,   // u64s != 2                 (dbde_util.cpp:335)
+    kStBadDepthCount = 2,    // nb != w*h                 (dbde_util.cpp:296)
+    kStBadMinCount = 4,      // nm != w*h                 (dbde_util.cpp:299)
+    kStBadWordCount = 8,     // sum(depth) != n64         (dbde_util.cpp:302-303)
+    kStDepthTooBig = 16,     // a depth byte > 8 (the reference does not reject this; we do)
+    kStTruncated = 32,       // record runs past the end of the stream buffer
+};
+
+size_t enc_smem_bytes(const PartGeom &g);
+size_t dec_smem_bytes(const PartGeom &g);
+cudaError_t launch_encode(const EncParams &P, bool fast, int num_sms, cudaStream_t stream);
+cudaError_t launch_decode_scan(const DecParams &P, cudaStream_t stream);
+cudaError_t launch_decode(const DecParams &P, bool fast, int num_sms, cudaStream_t stream);
+
+}  // namespace dbde

@@ -1,0 +1,118 @@
+/* dbde_b200.h -- the C ABI of the B200-native DBDE frame codec.
+ *
+ * This is the thin extern "C" layer beneath the reference's C++ entry points
+ * (include/dbde_util.h mirrors /root/reference/dbde_util.h:21-52 and forwards here).
+ * Plain pointers and sizes only.  Every entry point names the reference interface it replaces.
+ *
+ * On-disk layout (unchanged; README.md:27-67 of the reference, dbde_util.cpp:137-209):
+ *   file         := video_header(28) frame_record*
+ *   frame_record := I32 2 | U64 index | F64 0.0 | I32 wh | U8 depth[wh] | I32 wh | U8 min[wh]
+ *                   | I32 n64 | U64 words[n64]                      (w=ceil(W/8), h=ceil(H/8), wh=w*h)
+ * A "stream" below is frame records laid back to back (the file minus its 28-byte header).
+ *
+ * All functions return 0 on success or a negative dbde_b200_error / positive cudaError_t value;
+ * dbde_b200_last_error() describes the last failure on the calling thread.  There is NO CPU
+ * fallback: without a CUDA device of compute capability 10.x every call fails loudly.
+ */
+#ifndef DBDE_B200_H
+#define DBDE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBDE_B200_API __attribute__((visibility("default")))
+
+typedef struct dbde_b200_ctx dbde_b200_ctx;
+
+enum dbde_b200_error {
+    DBDE_B200_OK = 0,
+    DBDE_B200_E_INVALID = -1,      /* bad argument */
+    DBDE_B200_E_NO_DEVICE = -2,    /* no sm_100 device / CUDA runtime unusable */
+    DBDE_B200_E_CAPACITY = -3,     /* output buffer too small */
+    DBDE_B200_E_NOMEM = -4
+};
+
+/* per-frame decode status bits (0 = decoded); mirrors the reject paths of dbde_unpack_image /
+ * dbde_unpack_frame(_header), dbde_util.cpp:296,299,303,335 */
+#define DBDE_B200_ST_BAD_FRAME_HEADER 1u
+#define DBDE_B200_ST_BAD_DEPTH_COUNT 2u
+#define DBDE_B200_ST_BAD_MIN_COUNT 4u
+#define DBDE_B200_ST_BAD_WORD_COUNT 8u
+#define DBDE_B200_ST_DEPTH_TOO_BIG 16u   /* depth byte > 8: unpinned in the reference, rejected here */
+#define DBDE_B200_ST_TRUNCATED 32u
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* One context per GPU and per host thread (contexts are not thread-safe; distinct contexts are). */
+DBDE_B200_API int dbde_b200_create(int device, dbde_b200_ctx **out);
+DBDE_B200_API void dbde_b200_destroy(dbde_b200_ctx *ctx);
+DBDE_B200_API const char *dbde_b200_last_error(void);
+DBDE_B200_API int dbde_b200_device_count(void);
+
+/* ---- sizes (pure host arithmetic) ------------------------------------------------------------ */
+/* worst-case bytes of one frame record, 32 + 66*wh  (the `target` contract of dbde_pack_frame,
+ * dbde_util.h:26, which has no capacity argument) */
+DBDE_B200_API size_t dbde_b200_frame_record_bound(int W, int H);
+/* worst-case bytes of n frame records back to back, + 16 bytes of tail slack */
+DBDE_B200_API size_t dbde_b200_stream_bound(int W, int H, int nframes);
+
+/* ---- device memory / pinned host memory helpers ---------------------------------------------- */
+/* cudaMalloc on the context's device; the block is 256-byte aligned and 16-byte tail-padded so
+ * the kernels' 16-byte-aligned bulk copies may touch the aligned hull of any sub-range. */
+DBDE_B200_API int dbde_b200_device_alloc(dbde_b200_ctx *ctx, size_t bytes, void **out);
+DBDE_B200_API int dbde_b200_device_free(dbde_b200_ctx *ctx, void *p);
+DBDE_B200_API int dbde_b200_host_alloc(size_t bytes, void **out);        /* pinned */
+DBDE_B200_API int dbde_b200_host_free(void *p);
+DBDE_B200_API int dbde_b200_memcpy_h2d(dbde_b200_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+DBDE_B200_API int dbde_b200_memcpy_d2h(dbde_b200_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+
+/* ---- the hot path, device-resident ---------------------------------------------------------- */
+/* Batched dbde_pack_frame (dbde_util.cpp:190-196, which calls dbde_pack_image :137-180):
+ * encodes frames first_index .. first_index+nframes-1 and writes their records back to back at
+ * out_dev.  frame_offsets_dev receives nframes+1 byte offsets (record starts; the last entry is
+ * the total size).  frames_dev: nframes*W*H bytes, tightly packed rows (stride = W), as the
+ * reference's `image` argument.  Asynchronous on `stream` (a cudaStream_t, NULL = default).
+ * out_capacity must be >= dbde_b200_stream_bound(W, H, nframes). */
+DBDE_B200_API int dbde_b200_encode_device(dbde_b200_ctx *ctx, const uint8_t *frames_dev, int W, int H,
+                                          uint64_t first_index, int nframes, uint8_t *out_dev,
+                                          size_t out_capacity, uint64_t *frame_offsets_dev, void *stream);
+
+/* Batched dbde_unpack_frame (dbde_util.cpp:339-345 -> dbde_unpack_image :291-328): decodes the
+ * nframes records found at stream_dev + frame_offsets_dev[i] into frames_dev (nframes*W*H).
+ * status_dev[i] = 0 or DBDE_B200_ST_* bits; a rejected frame's image is left untouched, as in the
+ * reference.  indices_dev (may be NULL) receives each record's frame index. */
+DBDE_B200_API int dbde_b200_decode_device(dbde_b200_ctx *ctx, const uint8_t *stream_dev, size_t stream_bytes,
+                                          const uint64_t *frame_offsets_dev, int W, int H, int nframes,
+                                          uint8_t *frames_dev, uint32_t *status_dev, uint64_t *indices_dev,
+                                          void *stream);
+
+/* ---- the hot path, host buffers (H2D + kernels + D2H inside the call) ------------------------ */
+/* Same contracts with HOST pointers (pinned memory from dbde_b200_host_alloc streams fastest;
+ * pageable memory works).  Frames are processed in chunks through double-buffered device staging
+ * so copies and kernels overlap.  Synchronous: results are in host memory on return, like the
+ * reference's calls. */
+DBDE_B200_API int dbde_b200_encode_host(dbde_b200_ctx *ctx, const uint8_t *frames_host, int W, int H,
+                                        uint64_t first_index, int nframes, uint8_t *out_host,
+                                        size_t out_capacity, uint64_t *frame_offsets_host);
+DBDE_B200_API int dbde_b200_decode_host(dbde_b200_ctx *ctx, const uint8_t *stream_host, size_t stream_bytes,
+                                        const uint64_t *frame_offsets_host, int W, int H, int nframes,
+                                        uint8_t *frames_host, uint32_t *status_host, uint64_t *indices_host);
+
+/* Host-side frame indexer (the pointer chase dbde_walk_a_file does implicitly, dbde_util.cpp:408-421;
+ * next = cur + 32 + 2wh + 8*n64).  Fills up to max_frames+1 offsets; returns the frame count or < 0. */
+DBDE_B200_API long dbde_b200_index_stream(const uint8_t *stream_host, size_t stream_bytes, int W, int H,
+                                          uint64_t *frame_offsets, long max_frames);
+
+/* Tuning knob for the host path: frames per staged chunk (default: ~64 MiB of pixels). */
+DBDE_B200_API int dbde_b200_set_chunk_frames(dbde_b200_ctx *ctx, int frames);
+
+/* Launch accounting for benchmarks: kernels launched by this context since creation. */
+DBDE_B200_API uint64_t dbde_b200_kernel_launches(const dbde_b200_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

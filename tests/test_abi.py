@@ -1,0 +1,80 @@
+"""CPU tests of the drop-in boundary: the shared library builds, loads, and exports every symbol
+that include/*.h declares (no compute calls -- there is no GPU here), and refuses to run
+without a B200 instead of falling back."""
+import ctypes
+import importlib
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pkg = importlib.import_module("dbce-video-cpp_b200")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(pkg.LIB_PATH):
+        pkg.build()
+    return pkg.load()
+
+
+def test_c_abi_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "dbde_b200.h")).read()
+    declared = set(re.findall(r"\b(dbde_b200_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"dbde_b200_error"}
+    assert declared == set(pkg.C_SYMBOLS), declared ^ set(pkg.C_SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_cxx_dropin_symbols_match_reference_mangling(lib):
+    """The 15 functions of dbde_util.h must carry the reference's mangled names."""
+    hdr = open(os.path.join(ROOT, "include", "dbde_util.h")).read()
+    declared = set(re.findall(r"\b(dbde_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(pkg.CXX_SYMBOLS), declared ^ set(pkg.CXX_SYMBOLS)
+    for name, mangled in pkg.CXX_SYMBOLS.items():
+        assert getattr(lib, mangled) is not None, name
+
+
+def test_size_helpers_are_pure_host_arithmetic(lib):
+    assert lib.dbde_b200_frame_record_bound(2048, 2048) == 32 + 66 * 65536 == 4325408
+    assert lib.dbde_b200_frame_record_bound(1001, 1003) == 1047848
+    assert lib.dbde_b200_frame_record_bound(10, 10) == 296
+    assert lib.dbde_b200_stream_bound(10, 10, 3) == 3 * 296 + 16
+
+
+def test_index_stream_host_pointer_chase(lib):
+    """next = cur + 32 + 2wh + 8*n64 (dbde_util.cpp:301,327); pure host code."""
+    import numpy as np
+    import oracle
+    fr = oracle.gen_frames("mix", 3, 40, 24)
+    stream, sizes = oracle.port.pack_frames(fr, 0)
+    offs = np.zeros(8, dtype=np.uint64)
+    n = lib.dbde_b200_index_stream(stream.ctypes.data, stream.nbytes, 40, 24, offs.ctypes.data, 7)
+    assert n == 3
+    assert offs[:4].tolist() == [0] + np.cumsum(sizes).tolist()
+    # a torn last record is not indexed
+    n = lib.dbde_b200_index_stream(stream.ctypes.data, stream.nbytes - 1, 40, 24, offs.ctypes.data, 7)
+    assert n == 2
+
+
+def test_no_gpu_means_loud_failure_not_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = ctypes.c_void_p()
+    rc = lib.dbde_b200_create(0, ctypes.byref(h))
+    assert rc != 0 and not h.value
+    assert b"no CPU fallback" in lib.dbde_b200_last_error() or b"CUDA" in lib.dbde_b200_last_error()
+    with pytest.raises(pkg.DbdeError):
+        pkg.Codec(0)
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package may reference it."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "dbce-video-cpp_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert "import oracle" not in src and "oracle/" not in src.replace("never touches oracle/", ""), fn

@@ -1,0 +1,279 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI and the
+reference's C++ entry points, against the oracle (the compiled reference when oracle/_ref is
+there, else the pinned port) and the committed golden vectors.  Bit-exact: this is integer /
+byte work, so every comparison is equality."""
+import hashlib
+import importlib
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import golden_random_frames, rand_frame
+
+pytestmark = pytest.mark.gpu
+pkg = importlib.import_module("dbce-video-cpp_b200")
+ORA = oracle.best()
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a, dtype=np.uint8).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def codec():
+    c = pkg.Codec(0)        # raises without a B200: no fallback
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def dropin():
+    return pkg.DropIn()
+
+
+def roundtrip_check(codec, frames, first_index=0):
+    """encode on GPU == oracle bytes; decode on GPU == oracle pixels == source."""
+    N, H, W = frames.shape
+    want, sizes = ORA.pack_frames(frames, first_index)
+    got, offs = codec.encode_host(frames, first_index)
+    assert int(offs[N]) == len(want), (W, H, N)
+    assert offs[:N].tolist() == [0] + np.cumsum(sizes).tolist()[:-1]
+    assert (got == want).all(), (W, H, N, int(np.argmax(got != want)))
+    dec, status, index = codec.decode_host(want, offs[:N], W, H)
+    assert (status == 0).all()
+    assert index.tolist() == [first_index + i for i in range(N)]
+    assert (dec == frames).all(), (W, H, N)
+
+
+# ------------------------------------------------------------------ golden vectors
+def test_readme_10x10(codec, dropin, golden):
+    """BASELINE config 1."""
+    img = np.array(golden["readme"]["image"], dtype=np.uint8)
+    enc = dropin.pack_image(img)
+    assert enc.tobytes().hex() == golden["readme"]["pack_image"]
+    assert dropin.pack_frame(7, img).tobytes().hex() == golden["readme"]["pack_frame_index7"]
+    n, dec = dropin.unpack_image(enc, 10, 10)
+    assert n == 92 and (dec == img).all()
+    roundtrip_check(codec, img[None], 7)
+
+
+def test_kat_8x16_like_the_reference_test(dropin, golden):
+    """dbde_util_test.cpp:134-213 step for step, through the same C++ symbols."""
+    img = np.array(golden["kat_8x16"]["image"], dtype=np.uint8).reshape(8, 16)
+    stream = np.array(golden["kat_8x16"]["stream"], dtype=np.uint8)
+    n, vh = dropin.unpack_video_header(stream)
+    assert n == 28 and vh == (3, 8, 16, 1.0)
+    used, hdr, dec = dropin.unpack_frame(stream[28:], 16, 8)
+    assert used == 100 and hdr == (2, 1, 0) and (dec == img).all()
+    enc = np.concatenate([dropin.pack_video_header(3, 8, 16, 1.0), dropin.pack_frame(1, img)])
+    assert len(enc) == 128 and (enc == stream).all()
+
+
+def test_headers(dropin, golden):
+    assert dropin.pack_video_header(3, 10, 10, 30.0).tobytes().hex() == golden["headers"]["video_3_10_10_30hz"]
+    assert dropin.pack_frame_header(2, 5, 123456789012345).tobytes().hex() == golden["headers"]["frame_2_5_123456789012345"]
+
+
+def test_small_flat_and_single_tiles(dropin, golden):
+    s = golden["small_3x5"]
+    img = np.array(s["image"], dtype=np.uint8)
+    assert dropin.pack_image(img).tobytes().hex() == s["pack_image"]
+    flat = np.full((8, 8), golden["flat_8x8"]["value"], dtype=np.uint8)
+    assert dropin.pack_image(flat).tobytes().hex() == golden["flat_8x8"]["pack_image"]
+    for t in golden["single_tiles"]:
+        tile = np.full((8, 8), t["min"], dtype=np.uint8)
+        tile[3, 5] = t["min"] + t["range"]
+        tile[7, 7] = t["min"] + t["range"] // 2
+        r, pay = dropin.pack_8x8(tile)
+        assert r == t["ret"] and pay.tobytes().hex() == t["payload"], t
+        back = dropin.unpack_8x8(r >> 8, r & 0xFF, pay, stride=11)
+        assert (back == tile).all()
+
+
+def test_partial_tiles(dropin):
+    rng = np.random.default_rng(5)
+    for rm, dm in [(1, 1), (2, 8), (8, 2), (2, 2), (7, 3), (3, 7), (8, 7), (7, 8), (5, 5)]:
+        tile = rng.integers(0, 256, (8, 8), dtype=np.uint8) >> int(rng.integers(0, 6))
+        r0, p0 = ORA.pack_8x8_partial(tile, rm, dm)
+        r1, p1 = dropin.pack_8x8_partial(tile, rm, dm)
+        assert r0 == r1 and (p0 == p1).all(), (rm, dm)
+        crop = dropin.unpack_8x8_partial(r1 >> 8, r1 & 0xFF, p1, rm, dm, fill=0xCD)
+        assert (crop[:dm, :rm] == tile[:dm, :rm]).all()
+        assert (crop[dm:, :] == 0xCD).all() and (crop[:, rm:] == 0xCD).all()   # never writes outside the crop
+
+
+def test_golden_random_frames(dropin, golden):
+    for c, img in golden_random_frames(golden):
+        rec = dropin.pack_frame(c["index"], img)
+        assert len(rec) == c["record_len"] and sha(rec) == c["record_sha256"], (c["W"], c["H"])
+        used, hdr, dec = dropin.unpack_frame(rec, c["W"], c["H"])
+        assert used == len(rec) and hdr == (2, c["index"], 0) and (dec == img).all()
+
+
+def test_golden_synthetic_streams(codec, golden):
+    for s in golden["synthetic"]:
+        fr = oracle.gen_frames(s["kind"], s["n"], s["W"], s["H"], seed=s["seed"])
+        stream, offs = codec.encode_host(fr, 0)
+        assert np.diff(offs).astype(np.int64).tolist() == s["sizes"]
+        assert sha(stream) == s["stream_sha256"], s
+
+
+# ------------------------------------------------------------------ differential vs the oracle
+@pytest.mark.parametrize("W,H", [(8, 8), (16, 8), (1, 1), (3, 5), (7, 9), (9, 7), (17, 23), (64, 64), (100, 37),
+                                 (257, 129), (255, 8), (256, 16), (264, 24), (1001, 83), (2048, 16), (2056, 24),
+                                 (2049, 9), (4096, 8), (4104, 16), (520, 520)])
+def test_sizes_and_edges(codec, W, H):
+    rng = np.random.default_rng(W * 10007 + H)
+    frames = np.stack([rand_frame(rng, W, H, ["classes", "noise", "flat"][i % 3]) for i in range(3)])
+    roundtrip_check(codec, frames, first_index=1000)
+
+
+def test_every_depth_class_uniform(codec):
+    """a whole frame at each depth 0..8 (uniform-depth warps hit the worst staging strides)"""
+    rng = np.random.default_rng(11)
+    for k in range(9):
+        rg = (1 << k) - 1
+        mn = 0 if k == 8 else 10
+        fr = (mn + (rng.integers(0, 256, (2, 64, 512)) & rg)).astype(np.uint8)
+        fr[:, ::8, ::8] = mn
+        fr[:, ::8, 1::8] = mn + rg
+        roundtrip_check(codec, fr)
+
+
+def test_batches_and_chunking(codec):
+    """many frames, forced small chunks: chunk seams must not show in the stream"""
+    fr = oracle.gen_frames("mix", 37, 136, 72)
+    codec.set_chunk_frames(5)
+    try:
+        roundtrip_check(codec, fr, first_index=2 ** 40)
+    finally:
+        codec.set_chunk_frames(0)
+    roundtrip_check(codec, fr, first_index=2 ** 40)
+
+
+def test_synthetic_configs_small(codec):
+    """BASELINE configs 3 and 4 (odd 1001x1003 depth mix; low-entropy) + noise, against the oracle"""
+    roundtrip_check(codec, oracle.gen_frames("mix", 2, 1001, 1003))
+    roundtrip_check(codec, oracle.gen_frames("low", 1, 4096, 512))
+    roundtrip_check(codec, oracle.gen_frames("noise", 2, 2048, 256))
+    roundtrip_check(codec, oracle.gen_frames("micro", 2, 2048, 2048))
+
+
+def test_device_resident_api(codec):
+    """the batched device entry points on HBM-resident buffers, unaligned stream base included"""
+    W, H, N = 256, 128, 9
+    fr = oracle.gen_frames("mix", N, W, H)
+    want, sizes = ORA.pack_frames(fr, 3)
+    cap = codec.stream_bound(W, H, N)
+    d_fr = codec.device_alloc(fr.nbytes)
+    d_out = codec.device_alloc(cap + 64)
+    d_off = codec.device_alloc(8 * (N + 1))
+    d_dec = codec.device_alloc(fr.nbytes)
+    d_st = codec.device_alloc(4 * N)
+    d_ix = codec.device_alloc(8 * N)
+    try:
+        codec.h2d(d_fr, fr)
+        for shift in (0, 4, 12, 1, 2):            # 16-, 4-, 2- and 1-byte aligned payloads
+            codec.encode_device(d_fr, W, H, 3, N, d_out + shift, cap, d_off)
+            offs = codec.d2h(d_off, 8 * (N + 1), np.uint64)
+            assert int(offs[N]) == len(want)
+            got = codec.d2h(d_out + shift, len(want))
+            assert (got == want).all(), shift
+            codec.h2d(d_dec, np.zeros_like(fr))
+            codec.decode_device(d_out + shift, len(want), d_off, W, H, N, d_dec, d_st, d_ix)
+            assert (codec.d2h(d_st, 4 * N, np.uint32) == 0).all()
+            assert codec.d2h(d_ix, 8 * N, np.uint64).tolist() == list(range(3, 3 + N))
+            assert (codec.d2h(d_dec, fr.nbytes).reshape(fr.shape) == fr).all(), shift
+    finally:
+        for p in (d_fr, d_out, d_off, d_dec, d_st, d_ix):
+            codec.device_free(p)
+
+
+def test_invalid_streams_are_rejected_and_leave_the_image_untouched(codec, dropin):
+    """dbde_util.cpp:296,299,303 (+ header tag :335): status bits, image untouched, good frames
+    in the same batch still decode"""
+    W, H, N = 48, 40, 6
+    wh = 6 * 5
+    fr = oracle.gen_frames("mix", N, W, H)
+    stream, sizes = ORA.pack_frames(fr, 0)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    bad = stream.copy()
+    bad[int(offs[1]) + 20] += 1                 # nb != wh
+    bad[int(offs[2]) + 24 + wh] += 1            # nm != wh
+    bad[int(offs[3]) + 28 + 2 * wh] += 1        # n64 != sum(depth)
+    bad[int(offs[4])] = 9                       # frame tag != 2
+    dec, status, _ = codec.decode_host(bad, offs[:N], W, H, fill=0xCD)
+    assert status.tolist() == [0, pkg.ST_BAD_DEPTH_COUNT, pkg.ST_BAD_MIN_COUNT, pkg.ST_BAD_WORD_COUNT,
+                               pkg.ST_BAD_FRAME_HEADER, 0]
+    for i in range(N):
+        if status[i]:
+            assert (dec[i] == 0xCD).all()
+        else:
+            assert (dec[i] == fr[i]).all()
+    # a depth byte > 8 is rejected (documented deviation: the reference does not pin this case)
+    bad = stream.copy()
+    bad[int(offs[0]) + 24] = 9
+    _, status, _ = codec.decode_host(bad, offs[:N], W, H)
+    assert status[0] & pkg.ST_DEPTH_TOO_BIG
+    # truncated stream
+    _, status, _ = codec.decode_host(stream[:int(offs[N]) - 8], offs[:N], W, H)
+    assert status[N - 1] & pkg.ST_TRUNCATED and (status[:N - 1] == 0).all()
+    # the drop-in signatures: 0 / u64s == -1, pointer left just after the header (:342-343)
+    rec = ORA.pack_frame(3, fr[0])
+    b = rec.copy(); b[20] += 1
+    used, hdr, img = dropin.unpack_frame(b, W, H, fill=0xCD)
+    o_used, o_hdr, o_img = ORA.unpack_frame(b, W, H, fill=0xCD)
+    assert (used, hdr) == (o_used, o_hdr) == (20, (0xFFFFFFFF, 3, 0)) and (img == o_img).all()
+    n, img = dropin.unpack_image(b[20:], W, H, fill=0xCD)
+    assert n == 0 and (img == 0xCD).all()
+
+
+def test_full_size_properties(codec):
+    """BASELINE config 2 at full frame size: 2048x2048 micro, 24 frames: byte-equal to the
+    reference, decode(encode(x)) == x, and the stream indexes back to the same offsets."""
+    N, W, H = 24, 2048, 2048
+    fr = oracle.gen_frames("micro", N, W, H)
+    stream, offs = codec.encode_host(fr, 0)
+    if oracle.ref is not None:
+        want, sizes = oracle.ref.pack_frames(fr, 0)
+        assert len(want) == len(stream) and (want == stream).all()
+    assert codec.index_stream(stream, W, H).tolist() == offs.tolist()
+    dec, status, index = codec.decode_host(stream, offs[:N], W, H)
+    assert (status == 0).all() and index.tolist() == list(range(N)) and (dec == fr).all()
+    depth = stream[24:24 + 65536]
+    assert abs((depth == 3).mean() - 0.80) < 0.02           # SURVEY.md 8d histogram
+
+
+def test_gpu_synth_matches_cpu_generator(codec):
+    import ctypes as C
+    lib = C.CDLL(os.path.join(os.path.dirname(oracle.__file__), "libdbde_synth.so"))
+    lib.synth_frames_device.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    for kind, W, H in [("noise", 70, 33), ("micro", 512, 256), ("mix", 1001, 64), ("low", 256, 256)]:
+        n = 2
+        d = codec.device_alloc(n * W * H)
+        assert lib.synth_frames_device(oracle.KINDS[kind], 42, 5, n, W, H, d, None) == 0
+        got = codec.d2h(d, n * W * H).reshape(n, H, W)
+        codec.device_free(d)
+        assert (got == oracle.gen_frames(kind, n, W, H, seed=42, f0=5)).all(), kind
+
+
+def test_file_walker(dropin):
+    """dbde_start_file_walk / dbde_walk_a_file / dbde_end_file_walk on a written .dbde file,
+    including the tiny odd frames that overflow the reference's buffer estimate."""
+    for W, H, N, buffered in [(10, 10, 7, 2), (136, 72, 11, 4), (64, 64, 3, 8)]:
+        fr = oracle.gen_frames("noise" if W == 10 else "mix", N, W, H)
+        stream, _ = ORA.pack_frames(fr, 100)
+        with tempfile.NamedTemporaryFile(suffix=".dbde", delete=False) as f:
+            f.write(ORA.pack_video_header(3, H, W, 30.0).tobytes())
+            f.write(stream.tobytes())
+            path = f.name
+        try:
+            vh, frames = dropin.walk_file(path, buffered)
+            assert vh == (3, H, W, 30.0) and len(frames) == N
+            for i, (hdr, img) in enumerate(frames):
+                assert hdr == (2, 100 + i, 0) and (img == fr[i]).all()
+        finally:
+            os.unlink(path)
