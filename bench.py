@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""DBDE encode+decode benchmark on B200 (the contract in the task statement, tier framing (4)).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, sm_100a)
+  python bench.py --impl reference [...]                          the reference's CPU path
+
+Workload (BASELINE.json configs[1]): 2048x2048 U8 synthetic microscopy-like video, 1000 frames per
+GPU; one STEP = encode the whole batch, then decode it again (device-resident).  Metric: raw-pixel
+GB/s = pixels encoded + pixels decoded per second (2 * frames * W * H / step time), summed over
+GPUs; frames/s for each direction are reported next to it.  Frames are independent, so N GPUs
+take N disjoint frame ranges (weak scaling: 1000 frames each) with no data-path collective;
+torch.distributed (NCCL) is used only for the timing barrier and the max over ranks.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "dbde_encode_decode_raw_pixel_throughput"
+UNIT = "GB/s"
+W = H = 2048
+KIND = "micro"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=1000, help="frames per GPU per step")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kind", default=KIND, choices=["micro", "mix", "low", "noise"])
+    ap.add_argument("--width", type=int, default=W)
+    ap.add_argument("--height", type=int, default=H)
+    return ap.parse_args()
+
+
+def workload_config(a, extra=None):
+    cfg = {"workload": "%dx%d U8 synthetic '%s' video (SURVEY 8d, seed 42), %d frames per GPU, encode+decode per step"
+                       % (a.width, a.height, a.kind, a.frames),
+           "frames_per_gpu": a.frames, "width": a.width, "height": a.height, "generator": a.kind,
+           "sharding": "contiguous frame ranges per GPU, no collective",
+           "l2": "inputs (%.1f GB per direction) exceed the 126 MB L2; no explicit flush"
+                 % (a.frames * a.width * a.height / 1e9)}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, power, reasons = [], [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            # "under load": the upper half of the samples (the sampler also sees the idle edges)
+            load = sorted(sm)[len(sm) // 2:]
+            out.update(sm_mhz=float(np.median(load)), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(power))
+        return out
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_rates(frames, threads, target_s=1.0):
+    """Time the reference's own CPU implementation (oracle/_ref: dbde_util.cpp compiled unmodified)
+    on `threads` host threads over contiguous frame ranges.  -> dict of rates."""
+    import oracle
+    if oracle.ref is None:
+        raise RuntimeError("oracle/_ref/libdbde_ref.so missing: build it where /root/reference exists")
+    n, Hh, Ww = frames.shape
+    # calibrate repetitions so each direction runs for about target_s
+    s, slots, sizes = oracle.ref_encode_mt(frames, threads, 1)
+    reps_e = max(1, int(target_s / max(s, 1e-4)))
+    s_e, slots, sizes = oracle.ref_encode_mt(frames, threads, reps_e)
+    s, dec, bad = oracle.ref_decode_mt(slots, Ww, Hh, threads, 1)
+    reps_d = max(1, int(target_s / max(s, 1e-4)))
+    s_d, dec, bad = oracle.ref_decode_mt(slots, Ww, Hh, threads, reps_d)
+    assert bad == 0 and (dec == frames).all(), "reference round trip failed"
+    enc_fps, dec_fps = n * reps_e / s_e, n * reps_d / s_d
+    px = Ww * Hh
+    t_pair = 1.0 / enc_fps + 1.0 / dec_fps            # seconds to encode AND decode one frame
+    return {"encode_fps": enc_fps, "decode_fps": dec_fps, "value": 2 * px / t_pair / 1e9,
+            "cpu_seconds": threads * (s_e + s_d), "reps": [reps_e, reps_d], "sizes": sizes}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import synth
+    threads = os.cpu_count() or 1
+    nsample = min(a.frames, 64)
+    frames = synth.gen_frames(a.kind, nsample, a.width, a.height)
+    per = []
+    for _ in range(a.warmup):
+        cpu_reference_rates(frames, threads, target_s=0.2)
+    t0 = time.time()
+    for _ in range(a.steps):
+        per.append(cpu_reference_rates(frames, threads, target_s=0.5))
+    wall = time.time() - t0
+    val = float(np.mean([p["value"] for p in per]))
+    enc = float(np.mean([p["encode_fps"] for p in per]))
+    dec = float(np.mean([p["decode_fps"] for p in per]))
+    sample = "%d frames of the same workload, dbde_pack_frame then dbde_unpack_frame, ~0.5 s per direction per step" % nsample
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1000.0 * wall / max(a.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(a), "encode_fps": enc, "decode_fps": dec,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "unmodified dbde_util.cpp (g++ -O3 -march=corei7, SSE4.1) via oracle/_ref, %d std::threads over "
+                    "contiguous frame ranges; host only, no GPU" % threads}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import synth
+    pkg = importlib.import_module("dbce-video-cpp_b200")
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the DBDE B200 codec has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    codec = pkg.Codec(local)
+    Ww, Hh, N = a.width, a.height, a.frames
+    px = Ww * Hh
+    wh = ((Ww + 7) // 8) * ((Hh + 7) // 8)
+    f0 = rank * N                                    # this GPU's contiguous frame range
+
+    # ---- resident buffers (torch owns the device memory; the codec gets raw pointers)
+    cap = codec.stream_bound(Ww, Hh, N)
+    frames = torch.empty(N * px + 64, dtype=torch.uint8, device=dev)
+    stream_buf = torch.empty(cap + 64, dtype=torch.uint8, device=dev)
+    decoded = torch.empty(N * px + 64, dtype=torch.uint8, device=dev)
+    offs = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+    sizes = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+    status = torch.zeros(N, dtype=torch.int32, device=dev)
+    delta = (16 - (32 + 2 * wh) % 16) % 16           # puts every frame's U64 words on 8/16-byte boundaries
+    out_ptr = stream_buf.data_ptr() + delta
+    cs = torch.cuda.current_stream().cuda_stream
+    synth.gen_frames_device(a.kind, N, Ww, Hh, frames.data_ptr(), seed=42, f0=f0, stream=cs)
+    torch.cuda.synchronize()
+
+    def encode():
+        codec.encode_device(frames.data_ptr(), Ww, Hh, f0, N, out_ptr, cap, offs.data_ptr(), sizes.data_ptr(), cs)
+
+    def decode(total):
+        # the decoder reads each record from its slot (offs[i] = i * slot_stride)
+        codec.decode_device(out_ptr, cap, offs.data_ptr(), Ww, Hh, N, decoded.data_ptr(), status.data_ptr(), None, cs)
+
+    # ---- correctness gate before any timing: round trip + a sample against the oracle
+    encode()
+    torch.cuda.synchronize()
+    total = int(sizes[:N].sum().item())           # bytes of all records (what a file would hold)
+    decode(total)
+    torch.cuda.synchronize()
+    assert int(status.abs().sum().item()) == 0, "decode rejected frames"
+    assert torch.equal(frames[:N * px], decoded[:N * px]), "decode(encode(x)) != x"
+    n64_total = (total - N * (32 + 2 * wh)) // 8
+    alg_bytes = N * px + 2 * N * wh + 8 * n64_total   # per launch, same both directions
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up, then EXACTLY K timed steps
+    for _ in range(a.warmup):
+        encode(); decode(total)
+    barrier()
+    launches0 = codec.launches()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(a.steps)]
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for k in range(a.steps):
+        ev[k][0].record()
+        encode()
+        ev[k][1].record()
+        decode(total)
+        ev[k][2].record()
+    end.record()
+    barrier()
+    elapsed_ms = start.elapsed_time(end)
+    launches = codec.launches() - launches0
+    clocks = sampler.stop() if sampler else None
+    enc_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    dec_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    t = torch.tensor([elapsed_ms, enc_ms, dec_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms, enc_ms_max, dec_ms_max = [float(x) for x in t.tolist()]
+    ms_per_step = elapsed_ms / a.steps
+    value = world * 2 * N * px / (ms_per_step * 1e-3) / 1e9
+
+    # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region
+    e2e = None
+    if not a.no_e2e:
+        h_frames = codec.pinned(N * px)
+        h_stream = codec.pinned(cap)
+        h_dec = codec.pinned(N * px)
+        h_offs = np.zeros(N + 1, dtype=np.uint64)
+        h_status = np.zeros(N, dtype=np.uint32)
+        torch.cuda.synchronize()
+        codec.lib.dbde_b200_memcpy_d2h(codec.h, h_frames.ptr, frames.data_ptr(), N * px)
+
+        def e2e_step():
+            codec.encode_host_raw(h_frames.ptr, Ww, Hh, f0, N, h_stream.ptr, cap, h_offs.ctypes.data)
+            codec.decode_host_raw(h_stream.ptr, int(h_offs[N]), h_offs.ctypes.data, Ww, Hh, N, h_dec.ptr,
+                                  h_status.ctypes.data, None)
+
+        e2e_step()                                   # warm-up (allocates the staging slots)
+        assert int(h_offs[N]) == total and not h_status.any()
+        assert np.array_equal(h_dec.array, h_frames.array), "e2e round trip differs"
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dt = float(te.item())
+        e2e = {"value": world * 2 * N * px * a.e2e_steps / dt / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(N * px + total + 8 * N), "d2h_bytes_per_step": int(total + 8 * (N + 1) + N * px + 4 * N),
+               "steps": a.e2e_steps, "ms_per_step": 1000 * dt / a.e2e_steps,
+               "path": "dbde_b200_encode_host + dbde_b200_decode_host on pinned host buffers (chunked, 3 staging slots)"}
+        for b in (h_frames, h_stream, h_dec):
+            b.free()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (algorithmic bytes / CUDA-event duration)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    enc_gbs, dec_gbs = alg_bytes / (enc_ms * 1e-3) / 1e9, alg_bytes / (dec_ms * 1e-3) / 1e9
+    dom = "encode" if enc_ms >= dec_ms else "decode"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dom, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "dbde_%s_kernel" % dom, "achieved": enc_gbs if dom == "encode" else dec_gbs,
+                "peak": peak, "unit": "GB/s", "frac": (enc_gbs if dom == "encode" else dec_gbs) / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
+                "encode": {"ms": enc_ms, "GBps": enc_gbs, "frac": enc_gbs / peak},
+                "decode": {"ms": dec_ms, "GBps": dec_gbs, "frac": dec_gbs / peak,
+                           "note": "scan pre-pass + unpack kernel, timed together"}}
+
+    # ---- the reference's CPU path on this box's host cores, bounded sample
+    cpu = None
+    if not a.no_cpu_baseline:
+        try:
+            threads = os.cpu_count() or 1
+            ns = min(N, 64)
+            sample = frames[:ns * px].cpu().numpy().reshape(ns, Hh, Ww)
+            r = cpu_reference_rates(sample, threads, target_s=1.0)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "reference",
+                   "sample": "first %d frames of this rank's batch, dbde_pack_frame/dbde_unpack_frame via oracle/_ref, "
+                             "~1 s per direction (%.0f core-seconds)" % (ns, r["cpu_seconds"]),
+                   "encode_fps": r["encode_fps"], "decode_fps": r["decode_fps"]}
+        except Exception as ex:            # the baseline must never take the bench line down
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %s" % ex}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic", "config": workload_config(a, {"n_gpus": world}),
+            "encode_fps": world * N / (enc_ms_max * 1e-3), "decode_fps": world * N / (dec_ms_max * 1e-3),
+            "encode_raw_GBps": world * N * px / (enc_ms_max * 1e-3) / 1e9,
+            "decode_raw_GBps": world * N * px / (dec_ms_max * 1e-3) / 1e9,
+            "compressed_ratio": total / float(N * px), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "gpu_launches_note": "per step: 1 encode kernel + 2 decode kernels (scan, unpack); memset excluded",
+            "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    codec.close()
+    return 0
+
+
+if __name__ == "__main__":
+    args = parse()
+    sys.exit(run_reference(args) if args.impl == "reference" else run_ours(args))

@@ -14,7 +14,8 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdbde_b200.so")
+# DBDE_B200_LIB selects an alternative build of the SAME library (A/B profiling variants)
+LIB_PATH = os.environ.get("DBDE_B200_LIB") or os.path.join(HERE, "libdbde_b200.so")
 
 _u8p = C.POINTER(C.c_uint8)
 _u32p = C.POINTER(C.c_uint32)
@@ -26,7 +27,7 @@ ST_BAD_WORD_COUNT, ST_DEPTH_TOO_BIG, ST_TRUNCATED = 8, 16, 32
 # every extern "C" symbol include/dbde_b200.h declares
 C_SYMBOLS = [
     "dbde_b200_create", "dbde_b200_destroy", "dbde_b200_last_error", "dbde_b200_device_count",
-    "dbde_b200_frame_record_bound", "dbde_b200_stream_bound", "dbde_b200_device_alloc", "dbde_b200_device_free",
+    "dbde_b200_frame_record_bound", "dbde_b200_slot_stride", "dbde_b200_stream_bound", "dbde_b200_device_alloc", "dbde_b200_device_free",
     "dbde_b200_host_alloc", "dbde_b200_host_free", "dbde_b200_memcpy_h2d", "dbde_b200_memcpy_d2h",
     "dbde_b200_encode_device", "dbde_b200_decode_device", "dbde_b200_encode_host", "dbde_b200_decode_host",
     "dbde_b200_index_stream", "dbde_b200_set_chunk_frames", "dbde_b200_kernel_launches",
@@ -70,6 +71,8 @@ def load():
     lib.dbde_b200_last_error.restype = C.c_char_p
     lib.dbde_b200_frame_record_bound.restype = C.c_size_t
     lib.dbde_b200_frame_record_bound.argtypes = [C.c_int, C.c_int]
+    lib.dbde_b200_slot_stride.restype = C.c_size_t
+    lib.dbde_b200_slot_stride.argtypes = [C.c_int, C.c_int]
     lib.dbde_b200_stream_bound.restype = C.c_size_t
     lib.dbde_b200_stream_bound.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.dbde_b200_device_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
@@ -79,7 +82,7 @@ def load():
     lib.dbde_b200_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     lib.dbde_b200_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     lib.dbde_b200_encode_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int,
-                                            C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+                                            C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dbde_b200_decode_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int,
                                             C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dbde_b200_encode_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int,
@@ -144,6 +147,9 @@ class Codec:
     def stream_bound(self, W, H, n):
         return self.lib.dbde_b200_stream_bound(W, H, n)
 
+    def slot_stride(self, W, H):
+        return self.lib.dbde_b200_slot_stride(W, H)
+
     def pinned(self, nbytes):
         return PinnedArray(self.lib, nbytes)
 
@@ -171,9 +177,11 @@ class Codec:
         self._ck(self.lib.dbde_b200_set_chunk_frames(self.h, n), "set_chunk_frames")
 
     # ---- device-resident hot path (raw device pointers, asynchronous on `stream`)
-    def encode_device(self, frames_ptr, W, H, first_index, n, out_ptr, out_cap, offs_ptr, stream=0):
+    def encode_device(self, frames_ptr, W, H, first_index, n, out_ptr, out_cap, offs_ptr, sizes_ptr, stream=0,
+                      slot_stride=0):
+        """record i -> out_ptr + i*slot_stride; offs[i] = i*slot_stride, sizes[i] = record bytes"""
         self._ck(self.lib.dbde_b200_encode_device(self.h, frames_ptr, W, H, first_index, n, out_ptr, out_cap,
-                                                  offs_ptr, stream), "encode_device")
+                                                  slot_stride, offs_ptr, sizes_ptr, stream), "encode_device")
 
     def decode_device(self, stream_ptr, stream_bytes, offs_ptr, W, H, n, frames_ptr, status_ptr, index_ptr=None,
                       stream=0):

@@ -34,9 +34,11 @@ struct HostSlot {
     uint8_t *d_a = nullptr;      // encode: frames   | decode: stream bytes
     uint8_t *d_b = nullptr;      // encode: records  | decode: frames
     uint64_t *d_off = nullptr;
+    uint64_t *d_size = nullptr;
     uint32_t *d_status = nullptr;
     uint64_t *d_index = nullptr;
     uint64_t *h_off = nullptr;   // pinned
+    uint64_t *h_size = nullptr;  // pinned
     size_t cap_a = 0, cap_b = 0;
     int cap_n = 0;
     int n = 0, first = 0;
@@ -127,6 +129,8 @@ static void free_slot(HostSlot &s) {
     if (s.d_a) cudaFree(s.d_a);
     if (s.d_b) cudaFree(s.d_b);
     if (s.d_off) cudaFree(s.d_off);
+    if (s.d_size) cudaFree(s.d_size);
+    if (s.h_size) cudaFreeHost(s.h_size);
     if (s.d_status) cudaFree(s.d_status);
     if (s.d_index) cudaFree(s.d_index);
     if (s.h_off) cudaFreeHost(s.h_off);
@@ -159,8 +163,9 @@ extern "C" size_t dbde_b200_frame_record_bound(int W, int H) {
     const size_t wh = (size_t)((W + 7) / 8) * ((H + 7) / 8);
     return 32 + 66 * wh;
 }
+extern "C" size_t dbde_b200_slot_stride(int W, int H) { return (dbde_b200_frame_record_bound(W, H) + 15) / 16 * 16; }
 extern "C" size_t dbde_b200_stream_bound(int W, int H, int nframes) {
-    return dbde_b200_frame_record_bound(W, H) * (size_t)(nframes < 0 ? 0 : nframes) + 16;
+    return dbde_b200_slot_stride(W, H) * (size_t)(nframes < 0 ? 0 : nframes) + 16;
 }
 
 // ------------------------------------------------------------------ memory helpers
@@ -212,12 +217,17 @@ static int grow(void **p, size_t *have, size_t need) {
 // ------------------------------------------------------------------ device-resident hot path
 extern "C" int dbde_b200_encode_device(dbde_b200_ctx *c, const uint8_t *frames_dev, int W, int H,
                                        uint64_t first_index, int nframes, uint8_t *out_dev, size_t out_capacity,
-                                       uint64_t *frame_offsets_dev, void *stream) {
-    if (!c || !dims_ok(W, H, nframes) || (nframes > 0 && (!frames_dev || !out_dev || !frame_offsets_dev)))
+                                       size_t slot_stride, uint64_t *frame_offsets_dev, uint64_t *frame_sizes_dev,
+                                       void *stream) {
+    if (!c || !dims_ok(W, H, nframes) ||
+        (nframes > 0 && (!frames_dev || !out_dev || !frame_offsets_dev || !frame_sizes_dev)))
         return fail(DBDE_B200_E_INVALID, "encode_device: bad argument");
     if (nframes == 0) return 0;
-    if (out_capacity < dbde_b200_stream_bound(W, H, nframes) - 16)
-        return fail(DBDE_B200_E_CAPACITY, "encode_device: out_capacity < dbde_b200_stream_bound()");
+    if (slot_stride == 0) slot_stride = dbde_b200_slot_stride(W, H);
+    if (slot_stride < dbde_b200_frame_record_bound(W, H))
+        return fail(DBDE_B200_E_INVALID, "encode_device: slot_stride < dbde_b200_frame_record_bound()");
+    if (out_capacity < slot_stride * (size_t)nframes)
+        return fail(DBDE_B200_E_CAPACITY, "encode_device: out_capacity < nframes * slot_stride");
     CK(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     const bool fast = (W % 16 == 0) && (H % 8 == 0) && (((uintptr_t)frames_dev & 15) == 0);
@@ -225,17 +235,18 @@ extern "C" int dbde_b200_encode_device(dbde_b200_ctx *c, const uint8_t *frames_d
     P.g = make_geom(W, H, fast);
     const unsigned long long nparts = (unsigned long long)nframes * P.g.ppf;
     if (nparts >= 0xFFFFFFF0ull) return fail(DBDE_B200_E_INVALID, "encode_device: batch too large");
-    // scratch: [ticket | pad to 128][fstart: nframes u64][desc: nparts u64], zeroed per launch
-    const size_t sbytes = 128 + 8 * (size_t)nframes + 8 * (size_t)nparts;
+    // scratch: [ticket | pad to 128][desc: nparts u64], zeroed per launch
+    const size_t sbytes = 128 + 8 * (size_t)nparts;
     int rc = grow(&c->enc_scratch, &c->enc_scratch_bytes, sbytes);
     if (rc) return rc;
     CK(cudaMemsetAsync(c->enc_scratch, 0, sbytes, st));
     P.frames = frames_dev;
     P.out = out_dev;
+    P.slot_stride = slot_stride;
     P.frame_offsets = frame_offsets_dev;
+    P.frame_sizes = frame_sizes_dev;
     P.ticket = (unsigned int *)c->enc_scratch;
-    P.fstart = (uint64_t *)((uint8_t *)c->enc_scratch + 128);
-    P.desc = P.fstart + nframes;
+    P.desc = (uint64_t *)((uint8_t *)c->enc_scratch + 128);
     P.first_index = first_index;
     P.nframes = nframes;
     P.nparts = (unsigned)nparts;
@@ -306,11 +317,15 @@ static int ensure_slot(dbde_b200_ctx *c, HostSlot &s, size_t need_a, size_t need
     }
     if (s.cap_n < n) {
         if (s.d_off) CK(cudaFree(s.d_off));
+        if (s.d_size) CK(cudaFree(s.d_size));
+        if (s.h_size) CK(cudaFreeHost(s.h_size));
         if (s.d_status) CK(cudaFree(s.d_status));
         if (s.d_index) CK(cudaFree(s.d_index));
         if (s.h_off) CK(cudaFreeHost(s.h_off));
-        s.d_off = nullptr; s.d_status = nullptr; s.d_index = nullptr; s.h_off = nullptr;
+        s.d_off = nullptr; s.d_size = nullptr; s.h_size = nullptr; s.d_status = nullptr; s.d_index = nullptr; s.h_off = nullptr;
         CK(cudaMalloc(&s.d_off, 8 * (size_t)(n + 1)));
+        CK(cudaMalloc(&s.d_size, 8 * (size_t)(n + 1)));
+        CK(cudaHostAlloc(&s.h_size, 8 * (size_t)(n + 1), cudaHostAllocDefault));
         CK(cudaMalloc(&s.d_status, 4 * (size_t)n));
         CK(cudaMalloc(&s.d_index, 8 * (size_t)n));
         CK(cudaHostAlloc(&s.h_off, 8 * (size_t)(n + 1), cudaHostAllocDefault));
@@ -338,16 +353,37 @@ extern "C" int dbde_b200_encode_host(dbde_b200_ctx *c, const uint8_t *frames_hos
         if (rc) return rc;
     }
     const int nchunks = (nframes + chunk - 1) / chunk;
+    const size_t stride = dbde_b200_slot_stride(W, H);
     size_t out_pos = 0;
     int rc_all = 0;
-    // finish(): wait for a chunk's kernel, learn its size, queue its D2H at the running offset
+    // finish(): wait for a chunk's kernel, learn the record sizes, and queue the D2H copies that
+    // lay the records back to back at the running offset (the host-side concatenation).  Large
+    // records go slot by slot; small ones come back as one block and are compacted on the host.
+    std::vector<uint8_t> small;
     auto finish = [&](int ci) -> int {
         HostSlot &s = c->slots[ci % kHostSlots];
         CK(cudaEventSynchronize(s.ev));
-        const uint64_t total = s.h_off[s.n];
+        uint64_t total = 0;
+        for (int i = 0; i < s.n; i++) total += s.h_size[i];
         if (out_pos + total > out_capacity) return fail(DBDE_B200_E_CAPACITY, "encode_host: out_capacity too small");
-        CK(cudaMemcpyAsync(out_host + out_pos, s.d_b + delta, total, cudaMemcpyDeviceToHost, s.st));
-        for (int i = 0; i < s.n; i++) frame_offsets_host[s.first + i] = out_pos + s.h_off[i];
+        if (stride >= 65536) {
+            size_t pos = out_pos;
+            for (int i = 0; i < s.n; i++) {
+                CK(cudaMemcpyAsync(out_host + pos, s.d_b + delta + (size_t)i * stride, s.h_size[i], cudaMemcpyDeviceToHost, s.st));
+                frame_offsets_host[s.first + i] = pos;
+                pos += s.h_size[i];
+            }
+        } else {
+            small.resize(stride * (size_t)s.n);
+            CK(cudaMemcpyAsync(small.data(), s.d_b + delta, stride * (size_t)s.n, cudaMemcpyDeviceToHost, s.st));
+            CK(cudaStreamSynchronize(s.st));
+            size_t pos = out_pos;
+            for (int i = 0; i < s.n; i++) {
+                memcpy(out_host + pos, small.data() + (size_t)i * stride, s.h_size[i]);
+                frame_offsets_host[s.first + i] = pos;
+                pos += s.h_size[i];
+            }
+        }
         out_pos += total;
         return 0;
     };
@@ -359,9 +395,9 @@ extern "C" int dbde_b200_encode_host(dbde_b200_ctx *c, const uint8_t *frames_hos
         s.n = nframes - s.first < chunk ? nframes - s.first : chunk;
         CK(cudaMemcpyAsync(s.d_a, frames_host + px * s.first, px * s.n, cudaMemcpyHostToDevice, s.st));
         rc_all = dbde_b200_encode_device(c, s.d_a, W, H, first_index + s.first, s.n, s.d_b + delta,
-                                         need_b - 32, s.d_off, s.st);
+                                         need_b - 32, stride, s.d_off, s.d_size, s.st);
         if (rc_all) break;
-        CK(cudaMemcpyAsync(s.h_off, s.d_off, 8 * (size_t)(s.n + 1), cudaMemcpyDeviceToHost, s.st));
+        CK(cudaMemcpyAsync(s.h_size, s.d_size, 8 * (size_t)s.n, cudaMemcpyDeviceToHost, s.st));
         CK(cudaEventRecord(s.ev, s.st));
         if (pending >= 0) rc_all = finish(pending);
         pending = ci;

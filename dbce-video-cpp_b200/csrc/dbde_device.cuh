@@ -140,28 +140,48 @@ constexpr uint64_t kDescInvalid = 0, kDescAggregate = 1, kDescPrefix = 2;
 constexpr uint64_t kDescValueMask = (1ull << 62) - 1;
 __device__ __forceinline__ uint64_t desc_make(uint64_t status, uint64_t value) { return (status << 62) | value; }
 
-// Called by all 32 lanes of one warp.  `p` > 0.  Returns the exclusive prefix of partition p:
-// the sum of the aggregates of partitions [0, p).  Partition 0 publishes kDescPrefix directly.
-__device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t *desc, unsigned p, int lane) {
+// Called by all 32 lanes of one warp.  Chains restart at every frame (the reference zeroes n64
+// per frame, dbde_util.cpp:146): `first` is the frame's first partition, `p` > `first`.  Returns
+// the sum of the aggregates of partitions [first, p).  The first round reads the 32 nearest
+// predecessors (with frame-interleaved tickets the nearest one is normally already resolved);
+// later rounds read 128 at a time with four independent loads per lane.
+constexpr int kLookbackSub = 4;
+__device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t *desc, unsigned p, unsigned first, int lane) {
     uint64_t sum = 0;
     long long look = (long long)p - 1;
+    int nsub = 1;
     while (true) {
-        long long idx = look - lane;
-        uint64_t d = idx >= 0 ? ld_relaxed_u64(desc + idx) : desc_make(kDescPrefix, 0);
-        unsigned st = (unsigned)(d >> 62);
-        unsigned inval = __ballot_sync(0xffffffffu, st == kDescInvalid);
-        unsigned pre = __ballot_sync(0xffffffffu, st == kDescPrefix);
-        if (pre) {
-            int j = __ffs((int)pre) - 1;                 // nearest predecessor that already knows its prefix
-            if (inval & ((1u << j) - 1u)) { __nanosleep(20); continue; }   // a nearer one is not published yet
-            uint32_t part = lane < j ? (uint32_t)(d & kDescValueMask) : 0u; // aggregates are <= 2048 each
-            sum += __reduce_add_sync(0xffffffffu, part);                    // REDUX.SUM
-            sum += __shfl_sync(0xffffffffu, d, j) & kDescValueMask;
-            return sum;
+        uint64_t d[kLookbackSub];
+#pragma unroll
+        for (int j = 0; j < kLookbackSub; j++) {
+            const long long idx = look - 32 * j - lane;
+            d[j] = (j < nsub && idx >= (long long)first) ? ld_relaxed_u64(desc + idx) : desc_make(kDescPrefix, 0);
         }
-        if (inval) { __nanosleep(20); continue; }
-        sum += __reduce_add_sync(0xffffffffu, (uint32_t)(d & kDescValueMask));
-        look -= 32;
+        bool done = false, stall = false;
+        int consumed = 0;
+#pragma unroll
+        for (int j = 0; j < kLookbackSub; j++) {
+            if (done || stall || j >= nsub) continue;
+            const unsigned st = (unsigned)(d[j] >> 62);
+            const unsigned inval = __ballot_sync(0xffffffffu, st == kDescInvalid);
+            const unsigned pre = __ballot_sync(0xffffffffu, st == kDescPrefix);
+            if (pre) {
+                const int jn = __ffs((int)pre) - 1;      // nearest predecessor that knows its prefix
+                if (inval & ((1u << jn) - 1u)) { stall = true; continue; }   // a nearer one is unpublished
+                const uint32_t part = lane < jn ? (uint32_t)(d[j] & kDescValueMask) : 0u;   // aggregates <= 2048
+                sum += __reduce_add_sync(0xffffffffu, part);                               // REDUX.SUM
+                sum += __shfl_sync(0xffffffffu, d[j], jn) & kDescValueMask;
+                done = true;
+            } else if (inval) {
+                stall = true;
+            } else {
+                sum += __reduce_add_sync(0xffffffffu, (uint32_t)(d[j] & kDescValueMask));
+                consumed++;
+            }
+        }
+        if (done) return sum;
+        look -= 32 * consumed;                           // fully aggregated sub-windows are never re-read
+        nsub = kLookbackSub;
     }
 }
 

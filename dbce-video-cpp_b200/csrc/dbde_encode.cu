@@ -10,15 +10,18 @@
 //   warp 9  (scan)     : publishes the partition's depth sum, resolves its exclusive prefix with
 //                        a single-pass decoupled look-back, and hands the output address to the
 //                        tile warps; writes the frame's fixed fields (header, lengths, n64)
-// The look-back chain runs over the whole batch, so every frame record lands at its final
-// offset (frame f starts at sum of the sizes of frames < f) and the device buffer is the file
-// image minus the 28-byte video header.
+// Word offsets are per-frame quantities (the reference zeroes n64 per frame, dbde_util.cpp:146),
+// so there is one look-back chain per frame, and tickets are INTERLEAVED across the frames of the
+// batch (ticket t -> frame t mod N, partition t div N): the partitions in flight at any moment
+// belong to different frames, a partition's predecessor was finished a whole generation earlier,
+// and the look-back is one descriptor read instead of a convoy of L2 round trips.  Frame f's
+// record is written to its own slot (out + f * slot_stride); sizes go to frame_sizes[].
 #include "dbde_device.cuh"
 #include "dbde_kernels.h"
 
 namespace dbde {
 
-constexpr int kEncStages = 3;
+constexpr int kEncStages = 4;
 constexpr int kEncThreads = kTilesPerPart + 64;
 
 struct EncCtl {                 // per-stage control block, written by the producer warp
@@ -63,10 +66,13 @@ __global__ void __launch_bounds__(kEncThreads, 2) dbde_encode_kernel(const EncPa
             const int s = it % kEncStages;
             const uint32_t ph = (it / kEncStages) & 1;
             mbar_wait(&S.empty[s], ph ^ 1);
-            unsigned p = 0;
-            if (lane == 0) p = atomicAdd(P.ticket, 1u);
-            p = __shfl_sync(0xffffffffu, p, 0);
-            if (p >= P.nparts) {
+            unsigned t = 0;
+            if (lane == 0) t = atomicAdd(P.ticket, 1u);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            // frame-interleaved order: all frames' partition 0, then all frames' partition 1, ...
+            const unsigned tq = t / (unsigned)P.nframes;
+            const unsigned p = (t - tq * (unsigned)P.nframes) * (unsigned)g.ppf + tq;
+            if (t >= P.nparts) {
                 if (lane == 0) {
                     S.ctl[s].part = -1;
                     mbar_arrive(&S.full[s]);
@@ -113,8 +119,6 @@ __global__ void __launch_bounds__(kEncThreads, 2) dbde_encode_kernel(const EncPa
         }
     } else if (warp == kConsumerWarps + 1) {
         // ============================ scan warp ============================
-        int cached_f = -1;
-        uint64_t cached_start = 0;
         for (unsigned it = 0;; it++) {
             const int s = it % kEncStages;
             const uint32_t ph = (it / kEncStages) & 1;
@@ -126,38 +130,28 @@ __global__ void __launch_bounds__(kEncThreads, 2) dbde_encode_kernel(const EncPa
             mbar_wait(&S.aggbar[s], ph);
             uint32_t wt = lane < kConsumerWarps ? S.warptot[s][lane] : 0u;
             const uint64_t agg = __reduce_add_sync(0xffffffffu, wt);
-            uint64_t excl = 0;
-            if (p == 0) {
-                if (lane == 0) st_relaxed_u64(P.desc, desc_make(kDescPrefix, agg));
+            uint64_t excl = 0;                      // U64 words of this frame before this partition
+            if (pi.q == 0) {
+                if (lane == 0) st_relaxed_u64(P.desc + p, desc_make(kDescPrefix, agg));
             } else {
                 if (lane == 0) st_relaxed_u64(P.desc + p, desc_make(kDescAggregate, agg));
-                excl = lookback_exclusive(P.desc, p, lane);
+#ifdef DBDE_EXP_SKIP_LOOKBACK      // profiling-only variant (WRONG output): isolates the pipeline from the scan chain
+                excl = (uint64_t)pi.q * 700;
+#else
+                excl = lookback_exclusive(P.desc, p, p - (unsigned)pi.q, lane);
+#endif
                 if (lane == 0) st_relaxed_u64(P.desc + p, desc_make(kDescPrefix, excl + agg));
             }
-            // words written by all frames before this one
-            uint64_t fstart;
-            if (pi.q == 0) {
-                fstart = excl;
-                if (lane == 0) st_relaxed_u64(P.fstart + pi.f, (1ull << 63) | excl);
-            } else if (pi.f == cached_f) {
-                fstart = cached_start;
-            } else {
-                uint64_t v;
-                do { v = ld_relaxed_u64(P.fstart + pi.f); } while (!(v >> 63));
-                fstart = v & ~(1ull << 63);
-            }
-            cached_f = pi.f;
-            cached_start = fstart;
             const size_t fixed = 32 + 2 * (size_t)g.wh;     // frame header + lengths + planes
-            uint8_t *frame = P.out + (size_t)pi.f * fixed + 8 * fstart;
+            uint8_t *frame = P.out + (size_t)pi.f * P.slot_stride;
             if (lane == 0) {
                 S.base[s].frame = frame;
-                S.base[s].payload = frame + fixed + 8 * (excl - fstart);
+                S.base[s].payload = frame + fixed + 8 * excl;
                 mbar_arrive(&S.basebar[s]);
             }
             if (pi.q == g.ppf - 1) {
                 // last partition of the frame: the fixed fields (dbde_util.cpp:141-146,182-188,191)
-                const uint32_t n64 = (uint32_t)(excl + agg - fstart);
+                const uint32_t n64 = (uint32_t)(excl + agg);
                 const uint64_t index = P.first_index + (uint64_t)pi.f;
                 uint32_t b;      // lane i writes one byte of {I32 2 | U64 index | F64 0.0 | I32 wh} {I32 wh} {I32 n64}
                 uint8_t *dst;
@@ -169,19 +163,56 @@ __global__ void __launch_bounds__(kEncThreads, 2) dbde_encode_kernel(const EncPa
                 else { b = (n64 >> (8 * (lane - 28))) & 0xff; dst = frame + 28 + 2 * (size_t)g.wh + (lane - 28); }
                 *dst = (uint8_t)b;
                 if (lane == 0) {
-                    const uint64_t off = (uint64_t)(frame - P.out);
-                    P.frame_offsets[pi.f] = off;
-                    if (pi.f == P.nframes - 1) P.frame_offsets[P.nframes] = off + fixed + 8ull * n64;
+                    P.frame_offsets[pi.f] = (uint64_t)pi.f * P.slot_stride;
+                    P.frame_sizes[pi.f] = fixed + 8ull * n64;
                 }
             }
         }
     } else {
         // ============================ tile warps: one lane == one 8x8 tile ============================
+        // The copy-out of partition i is deferred until partition i+1 has been packed, so the
+        // scan warp's look-back for i overlaps the arithmetic of i+1.
         int sb = 0, stx = tid;                  // slot -> (band within partition, tile column)
         if (g.nseg == 1 && g.G > 1) {
             sb = tid / g.w;
             stx = tid - sb * g.w;
         }
+        // deferred partition: its depth/min stay in registers until its addresses are known
+        int d_s = -1, d_k = 0, d_tfirst = 0;
+        uint32_t d_mn = 0, d_ph = 0;
+        bool d_valid = false;
+
+        auto flush_deferred = [&]() {
+            uint8_t *stage = stages + (size_t)d_s * g.stage_bytes;
+            uint32_t total = 0;
+#pragma unroll
+            for (int wv = 0; wv < kConsumerWarps; wv++) total += S.warptot[d_s][wv];
+            mbar_wait(&S.basebar[d_s], d_ph);
+            uint8_t *frame = S.base[d_s].frame;
+            uint8_t *payload = S.base[d_s].payload;
+            // ---- depth and minimum planes (dbde_util.cpp:156-157)
+            if (d_valid) {
+                frame[24 + d_tfirst + tid] = (uint8_t)d_k;
+                frame[28 + (size_t)g.wh + d_tfirst + tid] = (uint8_t)d_mn;
+            }
+            // ---- coalesced copy-out of the partition's `total` words
+            const uint64_t *st64 = reinterpret_cast<const uint64_t *>(stage);
+            const uintptr_t ga = (uintptr_t)payload;
+            if ((ga & 7) == 0) {
+                for (uint32_t i = tid; i < total; i += kTilesPerPart) st_stream_u64(payload + 8 * (size_t)i, st64[swz(i)]);
+            } else if ((ga & 3) == 0) {
+                const uint32_t *st32 = reinterpret_cast<const uint32_t *>(stage);
+                for (uint32_t i = tid; i < 2 * total; i += kTilesPerPart)
+                    st_stream_u32(payload + 4 * (size_t)i, st32[2 * swz(i >> 1) + (i & 1)]);
+            } else {
+                for (uint32_t i = tid; i < 8 * total; i += kTilesPerPart) payload[i] = stage[8 * swz(i >> 3) + (i & 7)];
+            }
+            fence_proxy_async();        // my generic accesses to the stage precede the next TMA fill
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.empty[d_s]);
+            d_s = -1;
+        };
+
         for (unsigned it = 0;; it++) {
             const int s = it % kEncStages;
             const uint32_t ph = (it / kEncStages) & 1;
@@ -236,14 +267,14 @@ __global__ void __launch_bounds__(kEncThreads, 2) dbde_encode_kernel(const EncPa
                 S.warptot[s][warp] = incl;
                 mbar_arrive(&S.aggbar[s]);
             }
-            bar_consumers();            // every tile is in registers: the stage may be overwritten
+            // every tile of this partition is in registers (its stage may be overwritten) and every
+            // payload word of the deferred partition has been staged (it may be copied out)
+            bar_consumers();
             uint32_t off = incl - (uint32_t)k;
-            uint32_t total = 0;
 #pragma unroll
             for (int wv = 0; wv < kConsumerWarps; wv++) {
                 const uint32_t t = S.warptot[s][wv];
                 if (wv < warp) off += t;
-                total += t;
             }
             // ---- stage (4): pack (p - min) into k U64 words, staged (swizzled) in the dead pixel stage
             if (k > 0) {
@@ -264,33 +295,12 @@ __global__ void __launch_bounds__(kEncThreads, 2) dbde_encode_kernel(const EncPa
                     default: concat_fields<8>(q, store); break;
                 }
             }
-            bar_consumers();            // payload staged
-            mbar_wait(&S.basebar[s], ph);
-            uint8_t *frame = S.base[s].frame;
-            uint8_t *payload = S.base[s].payload;
-            // ---- depth and minimum planes (dbde_util.cpp:156-157)
-            if (valid) {
-                frame[24 + pi.tfirst + tid] = (uint8_t)k;
-                frame[28 + (size_t)g.wh + pi.tfirst + tid] = (uint8_t)mn;
-            }
-            // ---- coalesced copy-out of the partition's `total` words
-            {
-                const uint64_t *st64 = reinterpret_cast<const uint64_t *>(stage);
-                const uintptr_t ga = (uintptr_t)payload;
-                if ((ga & 7) == 0) {
-                    for (uint32_t i = tid; i < total; i += kTilesPerPart) st_stream_u64(payload + 8 * (size_t)i, st64[swz(i)]);
-                } else if ((ga & 3) == 0) {
-                    const uint32_t *st32 = reinterpret_cast<const uint32_t *>(stage);
-                    for (uint32_t i = tid; i < 2 * total; i += kTilesPerPart)
-                        st_stream_u32(payload + 4 * (size_t)i, st32[2 * swz(i >> 1) + (i & 1)]);
-                } else {
-                    for (uint32_t i = tid; i < 8 * total; i += kTilesPerPart)
-                        payload[i] = stage[8 * swz(i >> 3) + (i & 7)];
-                }
-            }
-            fence_proxy_async();        // my generic accesses to the stage precede the next TMA fill
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.empty[s]);
+            if (d_s >= 0) flush_deferred();
+            d_s = s; d_ph = ph; d_k = k; d_mn = mn; d_tfirst = pi.tfirst; d_valid = valid;
+        }
+        if (d_s >= 0) {
+            bar_consumers();            // the last partition's payload is fully staged
+            flush_deferred();
         }
     }
 }

@@ -7,10 +7,11 @@ namespace dbde {
 struct EncParams {
     PartGeom g;
     const uint8_t *frames;      // nframes * W * H, tightly packed, device
-    uint8_t *out;               // where frame record 0 starts, device
-    uint64_t *frame_offsets;    // nframes + 1 entries, device
-    uint64_t *desc;             // nparts look-back descriptors, zeroed
-    uint64_t *fstart;           // nframes frame-start slots, zeroed
+    uint8_t *out;               // slot of frame record 0, device; record f lives at out + f * slot_stride
+    uint64_t slot_stride;       // bytes between consecutive frame slots (>= 32 + 66*wh)
+    uint64_t *frame_offsets;    // nframes entries (= f * slot_stride), device
+    uint64_t *frame_sizes;      // nframes entries (record bytes), device
+    uint64_t *desc;             // nparts look-back descriptors (index f*ppf + q), zeroed
     unsigned int *ticket;       // zeroed
     uint64_t first_index;
     int nframes;

@@ -8,7 +8,10 @@
  *   file         := video_header(28) frame_record*
  *   frame_record := I32 2 | U64 index | F64 0.0 | I32 wh | U8 depth[wh] | I32 wh | U8 min[wh]
  *                   | I32 n64 | U64 words[n64]                      (w=ceil(W/8), h=ceil(H/8), wh=w*h)
- * A "stream" below is frame records laid back to back (the file minus its 28-byte header).
+ * A "stream" below is a byte buffer holding frame records plus a table of their offsets; records
+ * laid back to back are the file minus its 28-byte header.  The device encoder writes each record
+ * into its own fixed-stride SLOT (frames are independent, dbde_util.cpp:146 zeroes n64 per frame);
+ * the host entry points concatenate the slots back to back while copying them off the GPU.
  *
  * All functions return 0 on success or a negative dbde_b200_error / positive cudaError_t value;
  * dbde_b200_last_error() describes the last failure on the calling thread.  There is NO CPU
@@ -56,7 +59,10 @@ DBDE_B200_API int dbde_b200_device_count(void);
 /* worst-case bytes of one frame record, 32 + 66*wh  (the `target` contract of dbde_pack_frame,
  * dbde_util.h:26, which has no capacity argument) */
 DBDE_B200_API size_t dbde_b200_frame_record_bound(int W, int H);
-/* worst-case bytes of n frame records back to back, + 16 bytes of tail slack */
+/* default distance between the per-frame slots the device encoder writes: the record bound
+ * rounded up to 16 bytes */
+DBDE_B200_API size_t dbde_b200_slot_stride(int W, int H);
+/* bytes a stream buffer for n frames must hold: n * slot_stride + 16 bytes of tail slack */
 DBDE_B200_API size_t dbde_b200_stream_bound(int W, int H, int nframes);
 
 /* ---- device memory / pinned host memory helpers ---------------------------------------------- */
@@ -71,14 +77,17 @@ DBDE_B200_API int dbde_b200_memcpy_d2h(dbde_b200_ctx *ctx, void *dst_host, const
 
 /* ---- the hot path, device-resident ---------------------------------------------------------- */
 /* Batched dbde_pack_frame (dbde_util.cpp:190-196, which calls dbde_pack_image :137-180):
- * encodes frames first_index .. first_index+nframes-1 and writes their records back to back at
- * out_dev.  frame_offsets_dev receives nframes+1 byte offsets (record starts; the last entry is
- * the total size).  frames_dev: nframes*W*H bytes, tightly packed rows (stride = W), as the
- * reference's `image` argument.  Asynchronous on `stream` (a cudaStream_t, NULL = default).
- * out_capacity must be >= dbde_b200_stream_bound(W, H, nframes). */
+ * encodes frames first_index .. first_index+nframes-1.  Record i is written at
+ * out_dev + i * slot_stride (slot_stride 0 = dbde_b200_slot_stride(W, H)) and is byte-identical
+ * to what dbde_pack_frame writes; frame_offsets_dev[i] receives i * slot_stride and
+ * frame_sizes_dev[i] the record's size (nframes entries each).  frames_dev: nframes*W*H bytes,
+ * tightly packed rows (stride = W), as the reference's `image` argument.  Asynchronous on
+ * `stream` (a cudaStream_t, NULL = default).  out_capacity must be >= nframes * slot_stride.
+ * Fastest when (out_dev + 32 + 2*wh) is 16-byte aligned (U64 words land on 16-byte boundaries). */
 DBDE_B200_API int dbde_b200_encode_device(dbde_b200_ctx *ctx, const uint8_t *frames_dev, int W, int H,
                                           uint64_t first_index, int nframes, uint8_t *out_dev,
-                                          size_t out_capacity, uint64_t *frame_offsets_dev, void *stream);
+                                          size_t out_capacity, size_t slot_stride, uint64_t *frame_offsets_dev,
+                                          uint64_t *frame_sizes_dev, void *stream);
 
 /* Batched dbde_unpack_frame (dbde_util.cpp:339-345 -> dbde_unpack_image :291-328): decodes the
  * nframes records found at stream_dev + frame_offsets_dev[i] into frames_dev (nframes*W*H).
@@ -90,10 +99,12 @@ DBDE_B200_API int dbde_b200_decode_device(dbde_b200_ctx *ctx, const uint8_t *str
                                           void *stream);
 
 /* ---- the hot path, host buffers (H2D + kernels + D2H inside the call) ------------------------ */
-/* Same contracts with HOST pointers (pinned memory from dbde_b200_host_alloc streams fastest;
- * pageable memory works).  Frames are processed in chunks through double-buffered device staging
- * so copies and kernels overlap.  Synchronous: results are in host memory on return, like the
- * reference's calls. */
+/* Same codec with HOST pointers (pinned memory from dbde_b200_host_alloc streams fastest;
+ * pageable memory works).  Frames are processed in chunks through triple-buffered device staging
+ * so copies and kernels overlap.  encode_host lays the records BACK TO BACK in out_host (what a
+ * writer appends to the file after the video header) and fills frame_offsets_host[0..nframes]
+ * (record starts; the last entry is the total size).  Synchronous: results are in host memory
+ * on return, like the reference's calls. */
 DBDE_B200_API int dbde_b200_encode_host(dbde_b200_ctx *ctx, const uint8_t *frames_host, int W, int H,
                                         uint64_t first_index, int nframes, uint8_t *out_host,
                                         size_t out_capacity, uint64_t *frame_offsets_host);

@@ -1,6 +1,6 @@
 """ctypes bindings for the DBDE checkers -- TEST / BENCH INFRASTRUCTURE ONLY.
 
-`oracle.port`  : liboracle.so, the plain-C restatement (oracle/dbde_oracle.c) + CPU generators.
+`oracle.port`  : liboracle.so, the plain-C restatement (oracle/dbde_oracle.c).
 `oracle.ref`   : oracle/_ref/libdbde_ref.so, the UNMODIFIED reference (dbde_util.cpp) behind
                  ref_shim.cpp, or None when it has not been built.
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
@@ -13,7 +13,6 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-KINDS = {"noise": 0, "micro": 1, "mix": 2, "low": 3}
 
 _u8p = C.POINTER(C.c_uint8)
 _u64p = C.POINTER(C.c_uint64)
@@ -162,17 +161,6 @@ port = _Codec(_port_lib, "oracle_")
 
 _ref_lib = _load(os.path.join(HERE, "_ref", "libdbde_ref.so"))
 ref = _Codec(_ref_lib, "ref_") if _ref_lib is not None else None
-
-_port_lib.gen_frames.restype = None
-_port_lib.gen_frames.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, _u8p]
-
-
-def gen_frames(kind, nframes, W, H, seed=42, f0=0):
-    """CPU synthetic frames -> (N,H,W) u8."""
-    out = np.zeros((nframes, H, W), dtype=np.uint8)
-    _port_lib.gen_frames(KINDS[kind], seed, f0, nframes, W, H, _ptr(out))
-    return out
-
 
 def best():
     """The strongest checker available: the compiled reference, else the port."""

@@ -41,14 +41,16 @@ def test_size_helpers_are_pure_host_arithmetic(lib):
     assert lib.dbde_b200_frame_record_bound(2048, 2048) == 32 + 66 * 65536 == 4325408
     assert lib.dbde_b200_frame_record_bound(1001, 1003) == 1047848
     assert lib.dbde_b200_frame_record_bound(10, 10) == 296
-    assert lib.dbde_b200_stream_bound(10, 10, 3) == 3 * 296 + 16
+    assert lib.dbde_b200_slot_stride(10, 10) == 304 and lib.dbde_b200_slot_stride(2048, 2048) == 4325408
+    assert lib.dbde_b200_stream_bound(10, 10, 3) == 3 * 304 + 16
 
 
 def test_index_stream_host_pointer_chase(lib):
     """next = cur + 32 + 2wh + 8*n64 (dbde_util.cpp:301,327); pure host code."""
     import numpy as np
     import oracle
-    fr = oracle.gen_frames("mix", 3, 40, 24)
+    import synth
+    fr = synth.gen_frames("mix", 3, 40, 24)
     stream, sizes = oracle.port.pack_frames(fr, 0)
     offs = np.zeros(8, dtype=np.uint64)
     n = lib.dbde_b200_index_stream(stream.ctypes.data, stream.nbytes, 40, 24, offs.ctypes.data, 7)

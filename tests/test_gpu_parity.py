@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 
 import oracle
+import synth
 from conftest import golden_random_frames, rand_frame
 
 pytestmark = pytest.mark.gpu
@@ -115,7 +116,7 @@ def test_golden_random_frames(dropin, golden):
 
 def test_golden_synthetic_streams(codec, golden):
     for s in golden["synthetic"]:
-        fr = oracle.gen_frames(s["kind"], s["n"], s["W"], s["H"], seed=s["seed"])
+        fr = synth.gen_frames(s["kind"], s["n"], s["W"], s["H"], seed=s["seed"])
         stream, offs = codec.encode_host(fr, 0)
         assert np.diff(offs).astype(np.int64).tolist() == s["sizes"]
         assert sha(stream) == s["stream_sha256"], s
@@ -145,7 +146,7 @@ def test_every_depth_class_uniform(codec):
 
 def test_batches_and_chunking(codec):
     """many frames, forced small chunks: chunk seams must not show in the stream"""
-    fr = oracle.gen_frames("mix", 37, 136, 72)
+    fr = synth.gen_frames("mix", 37, 136, 72)
     codec.set_chunk_frames(5)
     try:
         roundtrip_check(codec, fr, first_index=2 ** 40)
@@ -156,40 +157,58 @@ def test_batches_and_chunking(codec):
 
 def test_synthetic_configs_small(codec):
     """BASELINE configs 3 and 4 (odd 1001x1003 depth mix; low-entropy) + noise, against the oracle"""
-    roundtrip_check(codec, oracle.gen_frames("mix", 2, 1001, 1003))
-    roundtrip_check(codec, oracle.gen_frames("low", 1, 4096, 512))
-    roundtrip_check(codec, oracle.gen_frames("noise", 2, 2048, 256))
-    roundtrip_check(codec, oracle.gen_frames("micro", 2, 2048, 2048))
+    roundtrip_check(codec, synth.gen_frames("mix", 2, 1001, 1003))
+    roundtrip_check(codec, synth.gen_frames("low", 1, 4096, 512))
+    roundtrip_check(codec, synth.gen_frames("noise", 2, 2048, 256))
+    roundtrip_check(codec, synth.gen_frames("micro", 2, 2048, 2048))
 
 
 def test_device_resident_api(codec):
-    """the batched device entry points on HBM-resident buffers, unaligned stream base included"""
+    """the batched device entry points on HBM-resident buffers: one slot per record, every slot
+    byte-identical to the oracle's record; unaligned slot bases and a custom stride included"""
     W, H, N = 256, 128, 9
-    fr = oracle.gen_frames("mix", N, W, H)
+    fr = synth.gen_frames("mix", N, W, H)
     want, sizes = ORA.pack_frames(fr, 3)
-    cap = codec.stream_bound(W, H, N)
+    starts = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     d_fr = codec.device_alloc(fr.nbytes)
-    d_out = codec.device_alloc(cap + 64)
-    d_off = codec.device_alloc(8 * (N + 1))
     d_dec = codec.device_alloc(fr.nbytes)
+    d_off = codec.device_alloc(8 * N)
+    d_sz = codec.device_alloc(8 * N)
     d_st = codec.device_alloc(4 * N)
     d_ix = codec.device_alloc(8 * N)
+    stride0 = codec.slot_stride(W, H)
+    cap = (stride0 + 48) * N + 64
+    d_out = codec.device_alloc(cap + 64)
     try:
         codec.h2d(d_fr, fr)
-        for shift in (0, 4, 12, 1, 2):            # 16-, 4-, 2- and 1-byte aligned payloads
-            codec.encode_device(d_fr, W, H, 3, N, d_out + shift, cap, d_off)
-            offs = codec.d2h(d_off, 8 * (N + 1), np.uint64)
-            assert int(offs[N]) == len(want)
-            got = codec.d2h(d_out + shift, len(want))
-            assert (got == want).all(), shift
+        for shift, stride in ((0, 0), (4, 0), (12, stride0 + 48), (1, stride0 + 3), (2, 0)):
+            st = stride or stride0
+            codec.h2d(d_out, np.full(cap + 64, 0xEE, dtype=np.uint8))
+            codec.encode_device(d_fr, W, H, 3, N, d_out + shift, cap, d_off, d_sz, slot_stride=stride)
+            offs = codec.d2h(d_off, 8 * N, np.uint64)
+            szs = codec.d2h(d_sz, 8 * N, np.uint64)
+            assert offs.tolist() == [i * st for i in range(N)] and szs.tolist() == sizes.tolist()
+            buf = codec.d2h(d_out + shift, st * N)
+            for i in range(N):
+                rec = buf[i * st:i * st + int(szs[i])]
+                assert (rec == want[starts[i]:starts[i + 1]]).all(), (shift, i)
+                assert (buf[i * st + int(szs[i]):(i + 1) * st] == 0xEE).all()      # nothing written past the record
             codec.h2d(d_dec, np.zeros_like(fr))
-            codec.decode_device(d_out + shift, len(want), d_off, W, H, N, d_dec, d_st, d_ix)
+            codec.decode_device(d_out + shift, st * N, d_off, W, H, N, d_dec, d_st, d_ix)
             assert (codec.d2h(d_st, 4 * N, np.uint32) == 0).all()
             assert codec.d2h(d_ix, 8 * N, np.uint64).tolist() == list(range(3, 3 + N))
             assert (codec.d2h(d_dec, fr.nbytes).reshape(fr.shape) == fr).all(), shift
     finally:
-        for p in (d_fr, d_out, d_off, d_dec, d_st, d_ix):
+        for p in (d_fr, d_out, d_off, d_sz, d_dec, d_st, d_ix):
             codec.device_free(p)
+
+
+def test_single_frame_many_partitions(codec):
+    """one big frame alone: every partition of the frame is in flight at once, so the per-frame
+    look-back chain has to resolve across concurrently running CTAs"""
+    for W, H in [(2048, 2048), (4096, 1024), (1001, 1003)]:
+        roundtrip_check(codec, synth.gen_frames("mix", 1, W, H))
+    roundtrip_check(codec, synth.gen_frames("micro", 3, 2048, 1024))
 
 
 def test_invalid_streams_are_rejected_and_leave_the_image_untouched(codec, dropin):
@@ -197,7 +216,7 @@ def test_invalid_streams_are_rejected_and_leave_the_image_untouched(codec, dropi
     in the same batch still decode"""
     W, H, N = 48, 40, 6
     wh = 6 * 5
-    fr = oracle.gen_frames("mix", N, W, H)
+    fr = synth.gen_frames("mix", N, W, H)
     stream, sizes = ORA.pack_frames(fr, 0)
     offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
     bad = stream.copy()
@@ -235,7 +254,7 @@ def test_full_size_properties(codec):
     """BASELINE config 2 at full frame size: 2048x2048 micro, 24 frames: byte-equal to the
     reference, decode(encode(x)) == x, and the stream indexes back to the same offsets."""
     N, W, H = 24, 2048, 2048
-    fr = oracle.gen_frames("micro", N, W, H)
+    fr = synth.gen_frames("micro", N, W, H)
     stream, offs = codec.encode_host(fr, 0)
     if oracle.ref is not None:
         want, sizes = oracle.ref.pack_frames(fr, 0)
@@ -248,23 +267,20 @@ def test_full_size_properties(codec):
 
 
 def test_gpu_synth_matches_cpu_generator(codec):
-    import ctypes as C
-    lib = C.CDLL(os.path.join(os.path.dirname(oracle.__file__), "libdbde_synth.so"))
-    lib.synth_frames_device.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     for kind, W, H in [("noise", 70, 33), ("micro", 512, 256), ("mix", 1001, 64), ("low", 256, 256)]:
         n = 2
         d = codec.device_alloc(n * W * H)
-        assert lib.synth_frames_device(oracle.KINDS[kind], 42, 5, n, W, H, d, None) == 0
+        synth.gen_frames_device(kind, n, W, H, d, seed=42, f0=5)
         got = codec.d2h(d, n * W * H).reshape(n, H, W)
         codec.device_free(d)
-        assert (got == oracle.gen_frames(kind, n, W, H, seed=42, f0=5)).all(), kind
+        assert (got == synth.gen_frames(kind, n, W, H, seed=42, f0=5)).all(), kind
 
 
 def test_file_walker(dropin):
     """dbde_start_file_walk / dbde_walk_a_file / dbde_end_file_walk on a written .dbde file,
     including the tiny odd frames that overflow the reference's buffer estimate."""
     for W, H, N, buffered in [(10, 10, 7, 2), (136, 72, 11, 4), (64, 64, 3, 8)]:
-        fr = oracle.gen_frames("noise" if W == 10 else "mix", N, W, H)
+        fr = synth.gen_frames("noise" if W == 10 else "mix", N, W, H)
         stream, _ = ORA.pack_frames(fr, 100)
         with tempfile.NamedTemporaryFile(suffix=".dbde", delete=False) as f:
             f.write(ORA.pack_video_header(3, H, W, 30.0).tobytes())

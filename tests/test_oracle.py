@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import oracle
+import synth
 from conftest import golden_random_frames
 
 CODECS = [("port", oracle.port)] + ([("ref", oracle.ref)] if oracle.ref is not None else [])
@@ -101,7 +102,7 @@ def test_golden_synthetic(golden, name, cd):
     for s in golden["synthetic"]:
         if s["W"] * s["H"] * s["n"] > 1100000 and name == "port":
             continue  # the bit-loop port is slow; the big case is covered by the reference codec
-        fr = oracle.gen_frames(s["kind"], s["n"], s["W"], s["H"], seed=s["seed"])
+        fr = synth.gen_frames(s["kind"], s["n"], s["W"], s["H"], seed=s["seed"])
         assert sha(fr) == s["frames_sha256"]
         stream, sizes = cd.pack_frames(fr, 0)
         assert [int(x) for x in sizes] == s["sizes"] and sha(stream) == s["stream_sha256"]
