@@ -11,8 +11,10 @@
 //   dbde_decode_kernel      : persistent, warp-specialised.  A producer warp bulk-TMAs each
 //                             partition's payload words + depth/min bytes into a ring of stages;
 //                             tile warps (one lane == one 8x8 tile) unpack with shifts and masks,
-//                             add the minimum, stage the 8-row band in shared memory and a bulk-TMA
-//                             store writes it out (generic path: cropped direct stores).
+//                             add the minimum and store their rows straight from registers: a
+//                             warp's 32 tiles make each row store one coalesced 256-byte segment,
+//                             so the warps never synchronise with each other (generic path:
+//                             cropped stores).
 #include "dbde_device.cuh"
 #include "dbde_kernels.h"
 
@@ -54,18 +56,55 @@ __global__ void __launch_bounds__(256) dbde_decode_scan_kernel(const DecParams P
     if (tid == 0) s_flag = 0;
     __syncthreads();
 
-    // phase 1: depth sum of every partition-warp (32 consecutive tiles of a partition)
+    // phase 1: depth sum of every partition-warp (32 consecutive tiles of a partition).  One warp
+    // takes a whole partition per step: lane l owns tiles 8l..8l+7 (8 depth bytes, summed with
+    // two IDP.4A), four lanes make one 32-tile item.  Four partitions are loaded before any is
+    // reduced so four global loads are in flight per lane.
     const uint8_t *dp = rec + 24;
     bool big = false;
-    for (int item = warp; item < nitems; item += 8) {
-        const int q = item >> 3, j = item & 7;
-        const PartInfo pi = part_info(g, (unsigned)q);
-        const int t = 32 * j + lane;
-        uint32_t d = 0;
-        if (t < pi.nt) d = dp[pi.tfirst + t];
-        if (d > 8) { big = true; d = 8; }
-        const uint32_t sum = __reduce_add_sync(0xffffffffu, d);
-        if (lane == 0) wp[item] = sum;
+    constexpr int kBatch = 4;
+    for (int q0 = warp * kBatch; q0 < g.ppf; q0 += 8 * kBatch) {
+        uint32_t lo[kBatch], hi[kBatch];
+#pragma unroll
+        for (int b = 0; b < kBatch; b++) {
+            lo[b] = hi[b] = 0;
+            const int q = q0 + b;
+            if (q < g.ppf) {
+                const PartInfo pi = part_info(g, (unsigned)q);
+                const uint8_t *src = dp + pi.tfirst + 8 * lane;
+                const int left = pi.nt - 8 * lane;               // tiles this lane really owns
+                if (left >= 8 && (((uintptr_t)src) & 3) == 0) {
+                    lo[b] = *reinterpret_cast<const uint32_t *>(src);
+                    hi[b] = *reinterpret_cast<const uint32_t *>(src + 4);
+                } else {
+                    for (int i = 0; i < 8; i++) {
+                        const uint32_t d = i < left ? src[i] : 0u;
+                        if (i < 4) lo[b] |= d << (8 * i);
+                        else hi[b] |= d << (8 * (i - 4));
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; b++) {
+            const int q = q0 + b;
+            // any byte > 8 ?  (low 7 bits + 0x77 carries into bit 7 when >= 9; bit 7 itself means >= 128)
+            const uint32_t over = ((((lo[b] & 0x7f7f7f7fu) + 0x77777777u) | lo[b]) |
+                                   (((hi[b] & 0x7f7f7f7fu) + 0x77777777u) | hi[b])) & 0x80808080u;
+            uint32_t sum;
+            if (over) {                                          // rare: clamp byte-wise like the slow path
+                big = true;
+                sum = 0;
+                for (int i = 0; i < 4; i++) {
+                    sum += min((lo[b] >> (8 * i)) & 0xffu, 8u) + min((hi[b] >> (8 * i)) & 0xffu, 8u);
+                }
+            } else {
+                sum = __dp4a(lo[b], 0x01010101u, __dp4a(hi[b], 0x01010101u, 0u));
+            }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            if (q < g.ppf && (lane & 3) == 0) wp[q * kConsumerWarps + (lane >> 2)] = sum;
+        }
     }
     if (big) atomicOr(&s_flag, 1u);
     __syncthreads();
@@ -116,6 +155,7 @@ __global__ void __launch_bounds__(256) dbde_decode_scan_kernel(const DecParams P
 struct DecCtl {
     int part;                  // -1 = no more work
     int skip;                  // frame was rejected by the scan: leave the image untouched
+    PartInfo pi;               // geometry of the partition (computed once, by the producer)
     uint32_t pres, kres, mres; // residual byte offsets of payload / depth / min inside their hulls
     uint32_t wbase[kConsumerWarps];   // word offset of each tile warp inside the partition's payload
 };
@@ -136,12 +176,11 @@ __device__ __forceinline__ void load_split(const uint8_t *pay, bool a4, uint32_t
 }
 
 template <bool FAST>
-__global__ void __launch_bounds__(kDecThreads, 2) dbde_decode_kernel(const DecParams P) {
+__global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     DecSmem &S = *reinterpret_cast<DecSmem *>(smem_raw);
     uint8_t *stages = smem_raw + ((sizeof(DecSmem) + 127) & ~127);
     const PartGeom &g = P.g;
-    uint8_t *obufs = stages + (size_t)kDecStages * kDecStageBytes;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const size_t fbytes = (size_t)g.W * g.H;
     const int nitems = g.ppf * kConsumerWarps;
@@ -210,7 +249,7 @@ __global__ void __launch_bounds__(kDecThreads, 2) dbde_decode_kernel(const DecPa
             const uint32_t len = nbytes ? (uint32_t)(a1 - a0) : 0u;
             const uint32_t res = (uint32_t)((uintptr_t)src - a0);
             if (lane < kConsumerWarps) S.ctl[s].wbase[lane] = v - v0;
-            if (lane == 0) { S.ctl[s].pres = res; S.ctl[s].part = (int)p; S.ctl[s].skip = 0; }
+            if (lane == 0) { S.ctl[s].pres = res; S.ctl[s].part = (int)p; S.ctl[s].skip = 0; S.ctl[s].pi = pi; }
             if (lane == 1) S.ctl[s].kres = res;
             if (lane == 2) S.ctl[s].mres = res;
             const uint32_t total = __reduce_add_sync(0xffffffffu, lane < 3 ? len : 0u);
@@ -226,7 +265,6 @@ __global__ void __launch_bounds__(kDecThreads, 2) dbde_decode_kernel(const DecPa
             sb = tid / g.w;
             stx = tid - sb * g.w;
         }
-        unsigned ob_it = 0;                     // counts DECODED partitions: picks the output buffer
         for (unsigned it = 0;; it++) {
             const int s = it % kDecStages;
             const uint32_t ph = (it / kDecStages) & 1;
@@ -238,7 +276,7 @@ __global__ void __launch_bounds__(kDecThreads, 2) dbde_decode_kernel(const DecPa
                 if (lane == 0) mbar_arrive(&S.empty[s]);
                 continue;
             }
-            const PartInfo pi = part_info(g, (unsigned)part);
+            const PartInfo pi = S.ctl[s].pi;
             const uint8_t *stage = stages + (size_t)s * kDecStageBytes;
             const bool valid = tid < pi.nt;
             const uint32_t pres = S.ctl[s].pres;
@@ -280,29 +318,12 @@ __global__ void __launch_bounds__(kDecThreads, 2) dbde_decode_kernel(const DecPa
 
             uint8_t *fptr = P.frames + (size_t)pi.f * fbytes;
             if (FAST) {
-                uint8_t *ob = obufs + (size_t)(ob_it++ & 1) * g.stage_bytes;
+                // no edges, 8-byte aligned rows: lane t stores 8 bytes of each row, a warp 256 contiguous bytes
                 if (valid) {
-                    uint8_t *base = ob + (size_t)(sb * 8) * g.pitch + stx * 8;
+                    uint8_t *base = fptr + (size_t)(8 * (pi.y0 + sb)) * g.W + 8 * (pi.tx0 + stx);
 #pragma unroll
                     for (int r = 0; r < 8; r++)
-                        *reinterpret_cast<uint2 *>(base + (size_t)r * g.pitch) = make_uint2(px[2 * r], px[2 * r + 1]);
-                }
-                fence_proxy_async();                       // rows visible to the bulk store
-                if (warp == 0) tma_store_wait_read<0>();   // the store that last read the OTHER buffer is done
-                bar_consumers();
-                if (warp == 0) {
-                    const int nrows = pi.nbands * 8;
-                    if (g.nseg == 1 && g.pitch == g.W) {
-                        // bands are contiguous both in shared and in global memory: one store per band
-                        if (lane < pi.nbands)
-                            tma_store_1d(fptr + (size_t)(8 * (pi.y0 + lane)) * g.W, ob + (size_t)(lane * 8) * g.pitch,
-                                         (uint32_t)(8 * g.W));
-                    } else {
-                        for (int row = lane; row < nrows; row += 32)
-                            tma_store_1d(fptr + (size_t)(8 * pi.y0 + row) * g.W + 8 * pi.tx0, ob + (size_t)row * g.pitch,
-                                         (uint32_t)(8 * pi.ntx));
-                    }
-                    tma_store_commit();
+                        st_stream_u64(base + (size_t)r * g.W, ((uint64_t)px[2 * r + 1] << 32) | px[2 * r]);
                 }
             } else if (valid) {
                 // crop the padding (dbde_util.cpp:281-289): only rows < H and columns < W are written
@@ -323,12 +344,12 @@ __global__ void __launch_bounds__(kDecThreads, 2) dbde_decode_kernel(const DecPa
                 }
             }
         }
-        if (FAST && warp == 0) tma_store_wait_all();       // shared memory must outlive the last bulk stores
     }
 }
 
 size_t dec_smem_bytes(const PartGeom &g) {
-    return ((sizeof(DecSmem) + 127) & ~(size_t)127) + (size_t)kDecStages * kDecStageBytes + 2 * (size_t)g.stage_bytes;
+    (void)g;
+    return ((sizeof(DecSmem) + 127) & ~(size_t)127) + (size_t)kDecStages * kDecStageBytes;
 }
 
 cudaError_t launch_decode_scan(const DecParams &P, cudaStream_t stream) {

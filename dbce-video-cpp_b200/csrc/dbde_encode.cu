@@ -26,6 +26,7 @@ constexpr int kEncThreads = kTilesPerPart + 64;
 
 struct EncCtl {                 // per-stage control block, written by the producer warp
     int part;                   // partition id, -1 = no more work
+    PartInfo pi;                // its geometry (computed once, by the producer)
     uint16_t rowoff[kMaxRowsPerPart];   // byte offset of each row's first pixel inside its smem row
 };
 struct EncBase {                // per-stage, written by the scan warp
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(kEncThreads, 2) dbde_encode_kernel(const EncPa
             __syncwarp();               // every lane's rowoff[] store precedes the release below
             if (lane == 0) {
                 S.ctl[s].part = (int)p;
+                S.ctl[s].pi = pi;
                 mbar_arrive_expect_tx(&S.full[s], total);
             }
             __syncwarp();
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(kEncThreads, 2) dbde_encode_kernel(const EncPa
             const int part = S.ctl[s].part;
             if (part < 0) break;
             const unsigned p = (unsigned)part;
-            const PartInfo pi = part_info(g, p);
+            const PartInfo pi = S.ctl[s].pi;
             mbar_wait(&S.aggbar[s], ph);
             uint32_t wt = lane < kConsumerWarps ? S.warptot[s][lane] : 0u;
             const uint64_t agg = __reduce_add_sync(0xffffffffu, wt);
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(kEncThreads, 2) dbde_encode_kernel(const EncPa
             mbar_wait(&S.full[s], ph);
             const int part = S.ctl[s].part;
             if (part < 0) break;
-            const PartInfo pi = part_info(g, (unsigned)part);
+            const PartInfo pi = S.ctl[s].pi;
             uint8_t *stage = stages + (size_t)s * g.stage_bytes;
             const bool valid = tid < pi.nt;
             const int asb = valid ? sb : 0, astx = valid ? stx : 0;   // idle lanes read (and discard) tile 0
