@@ -164,15 +164,40 @@ struct DecSmem {
     DecCtl ctl[kDecStages];
 };
 
-template <int K>
-__device__ __forceinline__ void load_split(const uint8_t *pay, bool a4, uint32_t (&q)[16]) {
+// ALIGN = 8: payload words are 8-byte aligned in shared memory (LDS.64), 4: 4-byte aligned
+// (LDS.32), 1: any byte offset (funnel-shifted pairs).  Uniform per partition.
+template <int K, int ALIGN>
+__device__ __forceinline__ void load_split(const uint8_t *pay, uint32_t (&q)[16]) {
     uint32_t x[16];
 #pragma unroll
     for (int j = 0; j < 16; j++) x[j] = 0;
+    if (ALIGN == 8) {
 #pragma unroll
-    for (int j = 0; j < 2 * K; j++)
-        x[j] = a4 ? reinterpret_cast<const uint32_t *>(pay)[j] : lds_u32_unaligned(pay + 4 * j);
+        for (int j = 0; j < K; j++) {
+            const uint2 v = reinterpret_cast<const uint2 *>(pay)[j];
+            x[2 * j] = v.x;
+            x[2 * j + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 2 * K; j++)
+            x[j] = ALIGN == 4 ? reinterpret_cast<const uint32_t *>(pay)[j] : lds_u32_unaligned(pay + 4 * j);
+    }
     split_fields<K>(x, q);
+}
+
+template <int ALIGN>
+__device__ __forceinline__ void load_split_any(int k, const uint8_t *pay, uint32_t (&q)[16]) {
+    switch (k) {
+        case 1: load_split<1, ALIGN>(pay, q); break;
+        case 2: load_split<2, ALIGN>(pay, q); break;
+        case 3: load_split<3, ALIGN>(pay, q); break;
+        case 4: load_split<4, ALIGN>(pay, q); break;
+        case 5: load_split<5, ALIGN>(pay, q); break;
+        case 6: load_split<6, ALIGN>(pay, q); break;
+        case 7: load_split<7, ALIGN>(pay, q); break;
+        default: load_split<8, ALIGN>(pay, q); break;
+    }
 }
 
 template <bool FAST>
@@ -293,17 +318,9 @@ __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecPa
             if (k > 0) {
                 uint32_t q[16];
                 const uint8_t *pay = stage + pres + 8 * (size_t)woff;
-                const bool a4 = (pres & 3u) == 0;
-                switch (k) {
-                    case 1: load_split<1>(pay, a4, q); break;
-                    case 2: load_split<2>(pay, a4, q); break;
-                    case 3: load_split<3>(pay, a4, q); break;
-                    case 4: load_split<4>(pay, a4, q); break;
-                    case 5: load_split<5>(pay, a4, q); break;
-                    case 6: load_split<6>(pay, a4, q); break;
-                    case 7: load_split<7>(pay, a4, q); break;
-                    default: load_split<8>(pay, a4, q); break;
-                }
+                if ((pres & 7u) == 0) load_split_any<8>(k, pay, q);
+                else if ((pres & 3u) == 0) load_split_any<4>(k, pay, q);
+                else load_split_any<1>(k, pay, q);
                 const uint32_t c1n = 256u - (1u << k), c2n = 65536u - (1u << (2 * k));
                 const uint32_t kmask2 = ((1u << k) - 1u) * 0x00010001u;
 #pragma unroll

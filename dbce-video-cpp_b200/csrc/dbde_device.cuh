@@ -240,25 +240,24 @@ __device__ __forceinline__ uint32_t spread4(uint32_t q, int k, uint32_t c1n, uin
     return p + odd * c1n;
 }
 
-// Concatenate sixteen 4K-bit fields LSB-first into K little-endian U64 words.  Everything is
-// compile-time after unrolling: constant shifts, unconditional stores.
+// Concatenate sixteen 4K-bit fields LSB-first into K little-endian U64 words (2K u32 halves).
+// Everything is compile-time after unrolling.  Fields never overlap, so "or" is "add" and a
+// field lands with ONE shift-add (IMAD/LEA) plus, when it straddles a 32-bit boundary, one
+// shift for the spill-over; the spill is always the first contributor of the next half-word.
 template <int K, typename Store>
 __device__ __forceinline__ void concat_fields(const uint32_t (&q)[16], Store &&store) {
-    uint64_t acc = 0;
-    int b = 0, n = 0;
+    uint32_t w[2 * K + 1];
+#pragma unroll
+    for (int n = 0; n < 2 * K + 1; n++) w[n] = 0;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
-        uint64_t v = q[i];
-        acc |= v << b;
-        if (b + 4 * K >= 64) {
-            store(n, acc);
-            n++;
-            acc = (b + 4 * K > 64) ? (v >> (64 - b)) : 0ull;
-            b = b + 4 * K - 64;
-        } else {
-            b += 4 * K;
-        }
+        const int bit = 4 * K * i, n = bit >> 5, sh = bit & 31;
+        if (sh == 0) w[n] = q[i];
+        else w[n] += q[i] << sh;
+        if (sh + 4 * K > 32) w[n + 1] = q[i] >> (32 - sh);
     }
+#pragma unroll
+    for (int n = 0; n < K; n++) store(n, w[2 * n], w[2 * n + 1]);
 }
 // inverse of concat_fields: K U64 words (as 2K u32) -> sixteen 4K-bit fields
 template <int K>
@@ -276,6 +275,8 @@ __device__ __forceinline__ void split_fields(const uint32_t (&x)[16], uint32_t (
 
 // staging swizzle at U64 granularity: spreads equal-depth lanes (stride K words) over the banks
 __device__ __forceinline__ uint32_t swz(uint32_t a) { return a ^ ((a >> 4) & 15u); }
+// the same permutation on BYTE offsets of U64 words (8*a -> 8*swz(a)): one shift + one fused and-xor
+__device__ __forceinline__ uint32_t swz_bytes(uint32_t byte_off) { return byte_off ^ ((byte_off >> 4) & 0x78u); }
 
 // unaligned-safe shared loads for the generic (odd width / odd offset) paths
 __device__ __forceinline__ uint32_t lds_u32_unaligned(const uint8_t *p) {

@@ -201,7 +201,16 @@ __global__ void __launch_bounds__(kEncThreads, 2) dbde_encode_kernel(const EncPa
             const uint64_t *st64 = reinterpret_cast<const uint64_t *>(stage);
             const uintptr_t ga = (uintptr_t)payload;
             if ((ga & 7) == 0) {
-                for (uint32_t i = tid; i < total; i += kTilesPerPart) st_stream_u64(payload + 8 * (size_t)i, st64[swz(i)]);
+                // 16-byte stores over the aligned middle, one 8-byte word at either end if needed
+                const uint32_t head = (uint32_t)((ga >> 3) & 1);          // words before 16-byte alignment
+                if (head && tid == 0 && total) st_stream_u64(payload, st64[swz(0)]);
+                const uint32_t npair = total > head ? (total - head) >> 1 : 0u;
+                for (uint32_t i = tid; i < npair; i += kTilesPerPart) {
+                    const uint32_t a = head + 2 * i;
+                    st_stream_v2u64(payload + 8 * (size_t)a, st64[swz(a)], st64[swz(a + 1)]);
+                }
+                const uint32_t done = head + 2 * npair;
+                if (done < total && tid == 1) st_stream_u64(payload + 8 * (size_t)done, st64[swz(done)]);
             } else if ((ga & 3) == 0) {
                 const uint32_t *st32 = reinterpret_cast<const uint32_t *>(stage);
                 for (uint32_t i = tid; i < 2 * total; i += kTilesPerPart)
@@ -284,8 +293,10 @@ __global__ void __launch_bounds__(kEncThreads, 2) dbde_encode_kernel(const EncPa
                 uint32_t q[16];
 #pragma unroll
                 for (int i = 0; i < 16; i++) q[i] = squeeze4(px[i], c1, c2);
-                uint64_t *st64 = reinterpret_cast<uint64_t *>(stage);
-                auto store = [&](int n, uint64_t v) { st64[swz(off + (uint32_t)n)] = v; };
+                const uint32_t off8 = 8u * off;
+                auto store = [&](int n, uint32_t lo, uint32_t hi) {
+                    *reinterpret_cast<uint2 *>(stage + swz_bytes(off8 + 8u * (uint32_t)n)) = make_uint2(lo, hi);
+                };
                 switch (k) {
                     case 1: concat_fields<1>(q, store); break;
                     case 2: concat_fields<2>(q, store); break;
