@@ -19,6 +19,8 @@
 #include "dbde_device.cuh"
 #include "dbde_kernels.h"
 
+#include <cstdlib>
+
 namespace dbde {
 
 constexpr int kEncStages = 4;
@@ -38,11 +40,15 @@ struct EncSmem {
     uint64_t full[kEncStages], empty[kEncStages], aggbar[kEncStages], basebar[kEncStages];
     EncCtl ctl[kEncStages];
     EncBase base[kEncStages];
-    uint32_t warptot[kEncStages][kConsumerWarps];
+    uint32_t warptot[kEncStages][kConsumerWarps];   // depth sum of each tile warp
+    uint32_t wbase[kEncStages][kConsumerWarps];     // its word offset inside the partition (scan warp)
 };
 
-template <bool FAST>
-__global__ void __launch_bounds__(kEncThreads, 2) dbde_encode_kernel(const EncParams P) {
+// FAST : 16-byte aligned rows, no partial tiles (W % 16 == 0, H % 8 == 0).
+// WST  : (FAST only) every tile warp covers 32 consecutive columns of ONE band, so its own slice
+//        of the pixel stage doubles as WARP-PRIVATE payload staging: no CTA barrier anywhere.
+template <bool FAST, bool WST>
+__global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     EncSmem &S = *reinterpret_cast<EncSmem *>(smem_raw);
     uint8_t *stages = smem_raw + ((sizeof(EncSmem) + 127) & ~127);
@@ -132,6 +138,11 @@ __global__ void __launch_bounds__(kEncThreads, 2) dbde_encode_kernel(const EncPa
             mbar_wait(&S.aggbar[s], ph);
             uint32_t wt = lane < kConsumerWarps ? S.warptot[s][lane] : 0u;
             const uint64_t agg = __reduce_add_sync(0xffffffffu, wt);
+            if (WST) {                               // exclusive prefix over the 8 tile warps
+                const uint32_t winc = warp_inclusive_scan(wt, lane);
+                if (lane < kConsumerWarps) S.wbase[s][lane] = winc - wt;
+                __syncwarp();
+            }
             uint64_t excl = 0;                      // U64 words of this frame before this partition
             if (pi.q == 0) {
                 if (lane == 0) st_relaxed_u64(P.desc + p, desc_make(kDescPrefix, agg));
@@ -181,14 +192,46 @@ __global__ void __launch_bounds__(kEncThreads, 2) dbde_encode_kernel(const EncPa
         }
         // deferred partition: its depth/min stay in registers until its addresses are known
         int d_s = -1, d_k = 0, d_tfirst = 0;
-        uint32_t d_mn = 0, d_ph = 0;
+        uint32_t d_mn = 0, d_ph = 0, d_wtot = 0;
         bool d_valid = false;
+
+        // payload staging address of U64 word `a` (swizzled against bank conflicts).
+        //   !WST: a = word index inside the partition, staged linearly from the stage base
+        //    WST: a = word index inside this WARP's payload; word (32*row + col) lives where the
+        //         warp's pixel row `row`, column `col` was (wb = the warp's first pixel byte)
+        auto word_ptr = [&](uint8_t *wb, uint32_t a) -> uint8_t * {
+            if (WST) {
+                const uint32_t x = swz(a);
+                return wb + (size_t)(x >> 5) * g.pitch + 8u * (x & 31u);
+            }
+            return wb + swz_bytes(8u * a);
+        };
+        // copy `n` staged words to global memory at `dst`, spread over `nthr` threads (rank `me`)
+        auto copy_out = [&](uint8_t *wb, uint8_t *dst, uint32_t n, uint32_t me, uint32_t nthr) {
+            const uintptr_t ga = (uintptr_t)dst;
+            if ((ga & 7) == 0) {
+                // 16-byte stores over the aligned middle, one 8-byte word at either end if needed
+                const uint32_t head = (uint32_t)((ga >> 3) & 1);
+                if (head && me == 0 && n) st_stream_u64(dst, *reinterpret_cast<const uint64_t *>(word_ptr(wb, 0)));
+                const uint32_t npair = n > head ? (n - head) >> 1 : 0u;
+                for (uint32_t i = me; i < npair; i += nthr) {
+                    const uint32_t a = head + 2 * i;
+                    st_stream_v2u64(dst + 8 * (size_t)a, *reinterpret_cast<const uint64_t *>(word_ptr(wb, a)),
+                                    *reinterpret_cast<const uint64_t *>(word_ptr(wb, a + 1)));
+                }
+                const uint32_t done = head + 2 * npair;
+                if (done < n && me == 1)
+                    st_stream_u64(dst + 8 * (size_t)done, *reinterpret_cast<const uint64_t *>(word_ptr(wb, done)));
+            } else if ((ga & 3) == 0) {
+                for (uint32_t i = me; i < 2 * n; i += nthr)
+                    st_stream_u32(dst + 4 * (size_t)i, *reinterpret_cast<const uint32_t *>(word_ptr(wb, i >> 1) + 4 * (i & 1)));
+            } else {
+                for (uint32_t i = me; i < 8 * n; i += nthr) dst[i] = word_ptr(wb, i >> 3)[i & 7];
+            }
+        };
 
         auto flush_deferred = [&]() {
             uint8_t *stage = stages + (size_t)d_s * g.stage_bytes;
-            uint32_t total = 0;
-#pragma unroll
-            for (int wv = 0; wv < kConsumerWarps; wv++) total += S.warptot[d_s][wv];
             mbar_wait(&S.basebar[d_s], d_ph);
             uint8_t *frame = S.base[d_s].frame;
             uint8_t *payload = S.base[d_s].payload;
@@ -197,26 +240,15 @@ __global__ void __launch_bounds__(kEncThreads, 2) dbde_encode_kernel(const EncPa
                 frame[24 + d_tfirst + tid] = (uint8_t)d_k;
                 frame[28 + (size_t)g.wh + d_tfirst + tid] = (uint8_t)d_mn;
             }
-            // ---- coalesced copy-out of the partition's `total` words
-            const uint64_t *st64 = reinterpret_cast<const uint64_t *>(stage);
-            const uintptr_t ga = (uintptr_t)payload;
-            if ((ga & 7) == 0) {
-                // 16-byte stores over the aligned middle, one 8-byte word at either end if needed
-                const uint32_t head = (uint32_t)((ga >> 3) & 1);          // words before 16-byte alignment
-                if (head && tid == 0 && total) st_stream_u64(payload, st64[swz(0)]);
-                const uint32_t npair = total > head ? (total - head) >> 1 : 0u;
-                for (uint32_t i = tid; i < npair; i += kTilesPerPart) {
-                    const uint32_t a = head + 2 * i;
-                    st_stream_v2u64(payload + 8 * (size_t)a, st64[swz(a)], st64[swz(a + 1)]);
-                }
-                const uint32_t done = head + 2 * npair;
-                if (done < total && tid == 1) st_stream_u64(payload + 8 * (size_t)done, st64[swz(done)]);
-            } else if ((ga & 3) == 0) {
-                const uint32_t *st32 = reinterpret_cast<const uint32_t *>(stage);
-                for (uint32_t i = tid; i < 2 * total; i += kTilesPerPart)
-                    st_stream_u32(payload + 4 * (size_t)i, st32[2 * swz(i >> 1) + (i & 1)]);
-            } else {
-                for (uint32_t i = tid; i < 8 * total; i += kTilesPerPart) payload[i] = stage[8 * swz(i >> 3) + (i & 7)];
+            // ---- coalesced copy-out
+            if (WST) {      // this warp's words, by this warp
+                uint8_t *wb = stage + (size_t)(sb * 8) * g.pitch + 8 * (stx - lane);
+                copy_out(wb, payload + 8 * (size_t)S.wbase[d_s][warp], d_wtot, (uint32_t)lane, 32u);
+            } else {        // the partition's words, by all tile warps
+                uint32_t total = 0;
+#pragma unroll
+                for (int wv = 0; wv < kConsumerWarps; wv++) total += S.warptot[d_s][wv];
+                copy_out(stage, payload, total, (uint32_t)tid, (uint32_t)kTilesPerPart);
             }
             fence_proxy_async();        // my generic accesses to the stage precede the next TMA fill
             __syncwarp();
@@ -274,28 +306,36 @@ __global__ void __launch_bounds__(kEncThreads, 2) dbde_encode_kernel(const EncPa
             if (!valid) { k = 0; mn = 0; }
             // ---- stage (3a): depth sums -> scan warp
             const uint32_t incl = warp_inclusive_scan((uint32_t)k, lane);
+            const uint32_t wtot = __shfl_sync(0xffffffffu, incl, 31);
             if (lane == 31) {
                 S.warptot[s][warp] = incl;
                 mbar_arrive(&S.aggbar[s]);
             }
-            // every tile of this partition is in registers (its stage may be overwritten) and every
-            // payload word of the deferred partition has been staged (it may be copied out)
-            bar_consumers();
-            uint32_t off = incl - (uint32_t)k;
+            uint32_t off = incl - (uint32_t)k;          // WST: word offset inside the warp's payload
+            uint8_t *wb;
+            if (WST) {
+                // the shuffles above already converged the warp: every lane's pixels are in registers,
+                // so the warp's own slice of the stage is dead and becomes its payload staging
+                wb = stage + (size_t)(sb * 8) * g.pitch + 8 * (stx - lane);
+            } else {
+                // every tile of this partition is in registers (its stage may be overwritten) and every
+                // payload word of the deferred partition has been staged (it may be copied out)
+                bar_consumers();
 #pragma unroll
-            for (int wv = 0; wv < kConsumerWarps; wv++) {
-                const uint32_t t = S.warptot[s][wv];
-                if (wv < warp) off += t;
+                for (int wv = 0; wv < kConsumerWarps; wv++) {
+                    const uint32_t t = S.warptot[s][wv];
+                    if (wv < warp) off += t;
+                }
+                wb = stage;
             }
-            // ---- stage (4): pack (p - min) into k U64 words, staged (swizzled) in the dead pixel stage
+            // ---- stage (4): pack (p - min) into k U64 words, staged (swizzled) in the dead pixel bytes
             if (k > 0) {
                 const uint32_t c1 = (1u << k) - 256u, c2 = (1u << (2 * k)) - 65536u;
                 uint32_t q[16];
 #pragma unroll
                 for (int i = 0; i < 16; i++) q[i] = squeeze4(px[i], c1, c2);
-                const uint32_t off8 = 8u * off;
                 auto store = [&](int n, uint32_t lo, uint32_t hi) {
-                    *reinterpret_cast<uint2 *>(stage + swz_bytes(off8 + 8u * (uint32_t)n)) = make_uint2(lo, hi);
+                    *reinterpret_cast<uint2 *>(word_ptr(wb, off + (uint32_t)n)) = make_uint2(lo, hi);
                 };
                 switch (k) {
                     case 1: concat_fields<1>(q, store); break;
@@ -308,11 +348,12 @@ __global__ void __launch_bounds__(kEncThreads, 2) dbde_encode_kernel(const EncPa
                     default: concat_fields<8>(q, store); break;
                 }
             }
+            if (WST) __syncwarp();      // the warp's payload is staged before any lane copies it out later
             if (d_s >= 0) flush_deferred();
-            d_s = s; d_ph = ph; d_k = k; d_mn = mn; d_tfirst = pi.tfirst; d_valid = valid;
+            d_s = s; d_ph = ph; d_k = k; d_mn = mn; d_tfirst = pi.tfirst; d_valid = valid; d_wtot = wtot;
         }
         if (d_s >= 0) {
-            bar_consumers();            // the last partition's payload is fully staged
+            if (!WST) bar_consumers();  // the last partition's payload is fully staged
             flush_deferred();
         }
     }
@@ -324,7 +365,13 @@ size_t enc_smem_bytes(const PartGeom &g) {
 
 cudaError_t launch_encode(const EncParams &P, bool fast, int num_sms, cudaStream_t stream) {
     const size_t smem = enc_smem_bytes(P.g);
-    auto kern = fast ? dbde_encode_kernel<true> : dbde_encode_kernel<false>;
+    // warp-private staging needs whole warps inside one band: every partition's ntx % 32 == 0
+    // Measured on B200 (micro-2048): CTA-wide staging 1.18 ms vs warp-private 1.24 ms per 1000 frames
+    // -- the barrier it removes is hidden by the other resident CTAs while its address math is not --
+    // so it stays an opt-in experiment (DBDE_B200_WST=1).
+    static const bool want_wst = getenv("DBDE_B200_WST") && atoi(getenv("DBDE_B200_WST")) != 0;
+    const bool wst = want_wst && fast && (P.g.w % 32 == 0);
+    auto kern = !fast ? dbde_encode_kernel<false, false> : (wst ? dbde_encode_kernel<true, true> : dbde_encode_kernel<true, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 0;
