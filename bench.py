@@ -61,47 +61,52 @@ def workload_config(a, extra=None):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons through NVML every ~2 ms on a thread (the timed
+    region is tens of milliseconds: nvidia-smi -lms cannot resolve it).  stop(t0, t1) keeps only the
+    samples taken inside the timed region [t0, t1] (time.perf_counter)."""
 
     def __init__(self, index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        import threading
+        self.samples = []
+        self.ok = False
+        self._stop = threading.Event()
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
         except Exception:
-            self.p = None
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
 
-    def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, power, reasons = [], [], [], set()
-        for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
             try:
-                sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
-            except ValueError:
-                continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.f.name)
-        if sm:
-            # "under load": the upper half of the samples (the sampler also sees the idle edges)
-            load = sorted(sm)[len(sm) // 2:]
-            out.update(sm_mhz=float(np.median(load)), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
-                       power_w_max=max(power))
+                self.samples.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                     nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0,
+                                     nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self, t0, t1):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.ok:
+            return out
+        self._stop.set()
+        self.t.join(timeout=2)
+        nv = self.nv
+        inside = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples[-3:]
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(n for n, b in bits.items() if any(s[3] & b for s in inside))
+        if inside:
+            out.update(sm_mhz=float(np.median([s[1] for s in inside])), sm_max_mhz=float(self.max_mhz), reasons=reasons,
+                       samples=len(inside), power_w_max=max(s[2] for s in inside))
         return out
 
 
@@ -227,6 +232,7 @@ def run_ours(a):
     sampler = ClockSampler(local) if rank == 0 else None
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(a.steps)]
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
     start.record()
     for k in range(a.steps):
         ev[k][0].record()
@@ -236,9 +242,10 @@ def run_ours(a):
         ev[k][2].record()
     end.record()
     barrier()
+    t_host1 = time.perf_counter()
     elapsed_ms = start.elapsed_time(end)
     launches = codec.launches() - launches0
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_host0, t_host1) if sampler else None
     enc_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
     dec_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
     t = torch.tensor([elapsed_ms, enc_ms, dec_ms], dtype=torch.float64, device=dev)

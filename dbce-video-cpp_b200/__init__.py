@@ -30,6 +30,7 @@ C_SYMBOLS = [
     "dbde_b200_frame_record_bound", "dbde_b200_slot_stride", "dbde_b200_stream_bound", "dbde_b200_device_alloc", "dbde_b200_device_free",
     "dbde_b200_host_alloc", "dbde_b200_host_free", "dbde_b200_memcpy_h2d", "dbde_b200_memcpy_d2h",
     "dbde_b200_encode_device", "dbde_b200_decode_device", "dbde_b200_encode_host", "dbde_b200_decode_host",
+    "dbde_b200_encode_host_sharded", "dbde_b200_decode_host_sharded",
     "dbde_b200_index_stream", "dbde_b200_set_chunk_frames", "dbde_b200_kernel_launches",
 ]
 # the reference's C++ entry points (include/dbde_util.h), by mangled name
@@ -89,6 +90,10 @@ def load():
                                           C.c_void_p, C.c_size_t, C.c_void_p]
     lib.dbde_b200_decode_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int,
                                           C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dbde_b200_encode_host_sharded.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int,
+                                                  C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.dbde_b200_decode_host_sharded.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
+                                                  C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dbde_b200_index_stream.restype = C.c_long
     lib.dbde_b200_index_stream.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_long]
     lib.dbde_b200_set_chunk_frames.argtypes = [C.c_void_p, C.c_int]
@@ -228,6 +233,38 @@ class Codec:
         if n < 0:
             raise DbdeError("index_stream failed")
         return offs[:n + 1].copy()
+
+
+def encode_host_sharded(codecs, frames, first_index=0):
+    """dbde_b200_encode_host_sharded over several Codec contexts -> (stream, offsets[N+1])."""
+    lib = codecs[0].lib
+    frames = np.ascontiguousarray(frames, dtype=np.uint8)
+    N, H, W = frames.shape
+    cap = codecs[0].stream_bound(W, H, N)
+    out = np.empty(cap, dtype=np.uint8)
+    offs = np.zeros(N + 1, dtype=np.uint64)
+    arr = (C.c_void_p * len(codecs))(*[c.h.value for c in codecs])
+    rc = lib.dbde_b200_encode_host_sharded(arr, len(codecs), frames.ctypes.data, W, H, first_index, N, out.ctypes.data,
+                                           cap, offs.ctypes.data)
+    if rc:
+        raise DbdeError("encode_host_sharded failed (%d): %s" % (rc, lib.dbde_b200_last_error().decode()))
+    return out[:int(offs[N])].copy(), offs
+
+
+def decode_host_sharded(codecs, stream, offsets, W, H):
+    lib = codecs[0].lib
+    stream = np.ascontiguousarray(stream, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    N = len(offsets)
+    frames = np.zeros((N, H, W), dtype=np.uint8)
+    status = np.zeros(N, dtype=np.uint32)
+    index = np.zeros(N, dtype=np.uint64)
+    arr = (C.c_void_p * len(codecs))(*[c.h.value for c in codecs])
+    rc = lib.dbde_b200_decode_host_sharded(arr, len(codecs), stream.ctypes.data, stream.nbytes, offsets.ctypes.data, W, H,
+                                           N, frames.ctypes.data, status.ctypes.data, index.ctypes.data)
+    if rc:
+        raise DbdeError("decode_host_sharded failed (%d): %s" % (rc, lib.dbde_b200_last_error().decode()))
+    return frames, status, index
 
 
 # ---------------------------------------------------------------------------------------------

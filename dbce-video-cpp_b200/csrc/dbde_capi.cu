@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace dbde;
@@ -483,6 +484,81 @@ extern "C" int dbde_b200_decode_host(dbde_b200_ctx *c, const uint8_t *stream_hos
     for (auto &s : c->slots)
         if (s.st) cudaStreamSynchronize(s.st);
     return rc_all;
+}
+
+// ------------------------------------------------------------------ multi-GPU sharding
+// contiguous frame ranges, one host thread per context; there is no cross-GPU exchange on the
+// data path, the host only prefix-sums the shard sizes
+extern "C" int dbde_b200_encode_host_sharded(dbde_b200_ctx **ctxs, int nctx, const uint8_t *frames_host, int W,
+                                             int H, uint64_t first_index, int nframes, uint8_t *out_host,
+                                             size_t out_capacity, uint64_t *frame_offsets_host) {
+    if (!ctxs || nctx < 1 || !dims_ok(W, H, nframes)) return fail(DBDE_B200_E_INVALID, "encode_host_sharded: bad argument");
+    if (nctx == 1 || nframes < nctx)
+        return dbde_b200_encode_host(ctxs[0], frames_host, W, H, first_index, nframes, out_host, out_capacity,
+                                     frame_offsets_host);
+    const size_t stride = dbde_b200_slot_stride(W, H), px = (size_t)W * H;
+    if (out_capacity < stride * (size_t)nframes)
+        return fail(DBDE_B200_E_CAPACITY, "encode_host_sharded: out_capacity < dbde_b200_stream_bound()");
+    std::vector<int> rc(nctx, 0), a(nctx + 1);
+    std::vector<std::string> err(nctx);
+    for (int g = 0; g <= nctx; g++) a[g] = (int)((long long)nframes * g / nctx);
+    std::vector<std::vector<uint64_t>> offs(nctx);
+    std::vector<std::thread> th;
+    for (int g = 0; g < nctx; g++) {
+        offs[g].resize(a[g + 1] - a[g] + 1);
+        th.emplace_back([&, g]() {
+            // shard g lands at its worst-case base; it is slid down once the earlier shards' sizes are known
+            rc[g] = dbde_b200_encode_host(ctxs[g], frames_host + px * a[g], W, H, first_index + a[g], a[g + 1] - a[g],
+                                          out_host + stride * (size_t)a[g], stride * (size_t)(a[g + 1] - a[g]),
+                                          offs[g].data());
+            if (rc[g]) err[g] = dbde_b200_last_error();
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int g = 0; g < nctx; g++)
+        if (rc[g]) return fail(rc[g], err[g].c_str());
+    size_t pos = 0;
+    for (int g = 0; g < nctx; g++) {
+        const int n = a[g + 1] - a[g];
+        const size_t bytes = offs[g][n];
+        const uint8_t *src = out_host + stride * (size_t)a[g];
+        if (out_host + pos != src) memmove(out_host + pos, src, bytes);
+        for (int i = 0; i < n; i++) frame_offsets_host[a[g] + i] = pos + offs[g][i];
+        pos += bytes;
+    }
+    frame_offsets_host[nframes] = pos;
+    return 0;
+}
+
+extern "C" int dbde_b200_decode_host_sharded(dbde_b200_ctx **ctxs, int nctx, const uint8_t *stream_host,
+                                             size_t stream_bytes, const uint64_t *frame_offsets_host, int W, int H,
+                                             int nframes, uint8_t *frames_host, uint32_t *status_host,
+                                             uint64_t *indices_host) {
+    if (!ctxs || nctx < 1 || !dims_ok(W, H, nframes)) return fail(DBDE_B200_E_INVALID, "decode_host_sharded: bad argument");
+    if (nctx == 1 || nframes < nctx)
+        return dbde_b200_decode_host(ctxs[0], stream_host, stream_bytes, frame_offsets_host, W, H, nframes, frames_host,
+                                     status_host, indices_host);
+    const size_t px = (size_t)W * H;
+    std::vector<int> rc(nctx, 0);
+    std::vector<std::string> err(nctx);
+    std::vector<std::thread> th;
+    for (int g = 0; g < nctx; g++) {
+        th.emplace_back([&, g]() {
+            const int a = (int)((long long)nframes * g / nctx), b = (int)((long long)nframes * (g + 1) / nctx);
+            // a shard's records end where the next shard's begin
+            const uint64_t base = frame_offsets_host[a];
+            const uint64_t end = b < nframes ? frame_offsets_host[b] : stream_bytes;
+            std::vector<uint64_t> rel(b - a);
+            for (int i = a; i < b; i++) rel[i - a] = frame_offsets_host[i] - base;
+            rc[g] = dbde_b200_decode_host(ctxs[g], stream_host + base, end - base, rel.data(), W, H, b - a,
+                                          frames_host + px * a, status_host + a, indices_host ? indices_host + a : nullptr);
+            if (rc[g]) err[g] = dbde_b200_last_error();
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int g = 0; g < nctx; g++)
+        if (rc[g]) return fail(rc[g], err[g].c_str());
+    return 0;
 }
 
 // ------------------------------------------------------------------ host indexer

@@ -276,6 +276,24 @@ def test_gpu_synth_matches_cpu_generator(codec):
         assert (got == synth.gen_frames(kind, n, W, H, seed=42, f0=5)).all(), kind
 
 
+def test_sharded_host_api_matches_single_context(codec):
+    """dbde_b200_{en,de}code_host_sharded: contiguous frame ranges over several contexts (here two
+    contexts on one GPU; on a multi-GPU box one per device) == the single-context stream"""
+    fr = synth.gen_frames("mix", 11, 264, 136)
+    want, sizes = ORA.pack_frames(fr, 50)
+    others = [pkg.Codec(0), pkg.Codec(0)]
+    try:
+        for group in ([codec] + others, others):
+            stream, offs = pkg.encode_host_sharded(group, fr, 50)
+            assert len(stream) == len(want) and (stream == want).all()
+            assert offs.tolist() == [0] + np.cumsum(sizes).tolist()
+            dec, status, index = pkg.decode_host_sharded(group, stream, offs[:-1], 264, 136)
+            assert (status == 0).all() and index.tolist() == list(range(50, 61)) and (dec == fr).all()
+    finally:
+        for c in others:
+            c.close()
+
+
 def test_file_walker(dropin):
     """dbde_start_file_walk / dbde_walk_a_file / dbde_end_file_walk on a written .dbde file,
     including the tiny odd frames that overflow the reference's buffer estimate."""
