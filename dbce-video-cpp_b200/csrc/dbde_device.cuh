@@ -79,16 +79,22 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// The suspend-time hint lets the hardware park the warp until the phase flips (or the hint expires)
+// instead of re-issuing YIELD/TRYWAIT/BRA: waiting warps then cost almost no issue slots.
+#ifndef DBDE_MBAR_SUSPEND_NS
+#define DBDE_MBAR_SUSPEND_NS 20000
+#endif
+constexpr uint32_t kMbarSuspendNs = DBDE_MBAR_SUSPEND_NS;
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendNs) : "memory");
 }
 // bulk TMA, global -> shared, completion on an mbarrier (SASS: UBLKCP).  16-byte aligned both sides.
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
@@ -128,6 +134,9 @@ __device__ __forceinline__ void st_stream_u64(void *p, uint64_t v) {
 }
 __device__ __forceinline__ void st_stream_v2u64(void *p, uint64_t a, uint64_t b) {
     asm volatile("st.global.cs.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void st_stream_v4u32(void *p, uint4 v) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void st_stream_u32(void *p, uint32_t v) {
     asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");

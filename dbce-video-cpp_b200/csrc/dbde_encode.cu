@@ -1,12 +1,12 @@
-// DBDE B200 encoder: raw U8 frames in HBM -> DBDE frame records laid back to back in HBM,
-// byte-identical to what dbde_pack_frame (dbde_util.cpp:190-196) writes frame after frame.
+// DBDE B200 encoder: raw U8 frames in HBM -> DBDE frame records in HBM, byte-identical to what
+// dbde_pack_frame (dbde_util.cpp:190-196) writes frame after frame.
 //
 // One persistent kernel, one pass over the pixels:
 //   warp 8  (producer) : claims partitions from an atomic ticket and bulk-TMAs their pixel rows
 //                        into a ring of shared-memory stages (mbarrier full/empty pipeline)
 //   warps 0-7 (tiles)  : one lane per 8x8 tile -- min, depth = bits(max-min), bit packing; the
-//                        payload words are staged in the (now dead) pixel stage and copied out
-//                        with coalesced stores
+//                        payload words are staged LINEARLY in the (now dead) pixel stage with
+//                        immediate-offset 8-byte stores and copied out with coalesced 16-byte stores
 //   warp 9  (scan)     : publishes the partition's depth sum, resolves its exclusive prefix with
 //                        a single-pass decoupled look-back, and hands the output address to the
 //                        tile warps; writes the frame's fixed fields (header, lengths, n64)
@@ -16,24 +16,32 @@
 // belong to different frames, a partition's predecessor was finished a whole generation earlier,
 // and the look-back is one descriptor read instead of a convoy of L2 round trips.  Frame f's
 // record is written to its own slot (out + f * slot_stride); sizes go to frame_sizes[].
+//
+// The kernel is issue-bound before it is HBM-bound (ncu: ~75 % issue-slot utilisation), so the
+// tile warps' loop is written for instruction count: no staging swizzle (a tile's k words go to
+// stage + 8*offset + {0, 8, 16, ...}), one 16-byte control read per partition, a REDUX for the
+// cross-warp prefix, and a copy-out that only distinguishes the parity of the first word.
 #include "dbde_device.cuh"
 #include "dbde_kernels.h"
-
-#include <cstdlib>
 
 namespace dbde {
 
 constexpr int kEncStages = 4;
 constexpr int kEncThreads = kTilesPerPart + 64;
 
-struct EncCtl {                 // per-stage control block, written by the producer warp
+struct alignas(16) EncCtl {     // per-stage control block, written by the producer warp
     int part;                   // partition id, -1 = no more work
-    PartInfo pi;                // its geometry (computed once, by the producer)
+    int f;                      // frame within the batch
+    int tfirst;                 // first tile's row-major index in the frame
+    int nt;                     // tiles in this partition
+    int q;                      // partition within the frame
+    int y0, tx0, pad;           // first band / first tile column (generic path only)
     uint16_t rowoff[kMaxRowsPerPart];   // byte offset of each row's first pixel inside its smem row
 };
-struct EncBase {                // per-stage, written by the scan warp
+struct alignas(16) EncBase {    // per-stage, written by the scan warp
     uint8_t *frame;             // where this frame's record starts
-    uint8_t *payload;           // where this partition's first U64 word goes
+    uint32_t excl;              // U64 words of this frame before this partition
+    uint32_t nwords;            // U64 words of this partition
 };
 
 struct EncSmem {
@@ -41,13 +49,60 @@ struct EncSmem {
     EncCtl ctl[kEncStages];
     EncBase base[kEncStages];
     uint32_t warptot[kEncStages][kConsumerWarps];   // depth sum of each tile warp
-    uint32_t wbase[kEncStages][kConsumerWarps];     // its word offset inside the partition (scan warp)
 };
 
+// Copy `n` staged U64 words (linear at `stage`) to global memory at `dst`; thread `me` of 256.
+__device__ __forceinline__ void enc_copy_out(const uint8_t *stage, uint8_t *dst, uint32_t n, uint32_t me) {
+    const uintptr_t ga = (uintptr_t)dst;
+    if ((ga & 7) == 0) {
+        // 16-byte stores over the aligned middle, one 8-byte word at either end if needed
+        const uint32_t head = (uint32_t)(ga >> 3) & 1u;
+        if (n <= head) {
+            if (n && me == 0) st_stream_u64(dst, *reinterpret_cast<const uint64_t *>(stage));
+            return;
+        }
+        const uint32_t npair = (n - head) >> 1;
+        const uint8_t *sp = stage + 8 * head + 16 * me;
+        uint8_t *dp = dst + 8 * head + 16 * me;
+        if (head == 0) {
+            for (uint32_t i = me; i < npair; i += kTilesPerPart, sp += 16 * kTilesPerPart, dp += 16 * kTilesPerPart)
+                st_stream_v4u32(dp, *reinterpret_cast<const uint4 *>(sp));
+        } else {
+            if (me == 0) st_stream_u64(dst, *reinterpret_cast<const uint64_t *>(stage));
+            for (uint32_t i = me; i < npair; i += kTilesPerPart, sp += 16 * kTilesPerPart, dp += 16 * kTilesPerPart) {
+                const uint2 a = *reinterpret_cast<const uint2 *>(sp), b = *reinterpret_cast<const uint2 *>(sp + 8);
+                st_stream_v4u32(dp, make_uint4(a.x, a.y, b.x, b.y));
+            }
+        }
+        const uint32_t done = head + 2 * npair;
+        if (done < n && me == 32) st_stream_u64(dst + 8 * (size_t)done, *reinterpret_cast<const uint64_t *>(stage + 8 * done));
+    } else if ((ga & 3) == 0) {
+        for (uint32_t i = me; i < 2 * n; i += kTilesPerPart)
+            st_stream_u32(dst + 4 * (size_t)i, *reinterpret_cast<const uint32_t *>(stage + 4 * i));
+    } else {
+        for (uint32_t i = me; i < 8 * n; i += kTilesPerPart) dst[i] = stage[i];
+    }
+}
+
+// depth 8: the words are the (p - min) rows themselves (dbde_util.cpp:57-64).  Equal-depth
+// neighbours sit 64 bytes apart -- an 8-way bank conflict for 8-byte stores -- so the 64 bytes go
+// out as 16-byte stores around the 16-byte boundary nearest to the tile's first word (4-way).
+__device__ __forceinline__ void enc_store_depth8(const uint32_t (&w)[16], uint8_t *wb, uint32_t off) {
+    if (off & 1u) {
+        *reinterpret_cast<uint2 *>(wb) = make_uint2(w[0], w[1]);
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            *reinterpret_cast<uint4 *>(wb + 8 + 16 * j) = make_uint4(w[4 * j + 2], w[4 * j + 3], w[4 * j + 4], w[4 * j + 5]);
+        *reinterpret_cast<uint2 *>(wb + 56) = make_uint2(w[14], w[15]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            *reinterpret_cast<uint4 *>(wb + 16 * j) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+    }
+}
+
 // FAST : 16-byte aligned rows, no partial tiles (W % 16 == 0, H % 8 == 0).
-// WST  : (FAST only) every tile warp covers 32 consecutive columns of ONE band, so its own slice
-//        of the pixel stage doubles as WARP-PRIVATE payload staging: no CTA barrier anywhere.
-template <bool FAST, bool WST>
+template <bool FAST>
 __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     EncSmem &S = *reinterpret_cast<EncSmem *>(smem_raw);
@@ -108,7 +163,7 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
                         const uintptr_t a1 = ((uintptr_t)a + rowbytes + 15) & ~(uintptr_t)15;
                         src[j] = (const uint8_t *)a0;
                         len[j] = (uint32_t)(a1 - a0);
-                        S.ctl[s].rowoff[row] = (uint16_t)((uintptr_t)a - a0);
+                        if (!FAST) S.ctl[s].rowoff[row] = (uint16_t)((uintptr_t)a - a0);
                     }
                 }
                 mybytes += len[j];
@@ -116,8 +171,8 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
             const uint32_t total = __reduce_add_sync(0xffffffffu, mybytes);
             __syncwarp();               // every lane's rowoff[] store precedes the release below
             if (lane == 0) {
-                S.ctl[s].part = (int)p;
-                S.ctl[s].pi = pi;
+                *reinterpret_cast<int4 *>(&S.ctl[s].part) = make_int4((int)p, pi.f, pi.tfirst, pi.nt);
+                *reinterpret_cast<int4 *>(&S.ctl[s].q) = make_int4(pi.q, pi.y0, pi.tx0, 0);
                 mbar_arrive_expect_tx(&S.full[s], total);
             }
             __syncwarp();
@@ -131,41 +186,32 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
             const int s = it % kEncStages;
             const uint32_t ph = (it / kEncStages) & 1;
             mbar_wait(&S.full[s], ph);
-            const int part = S.ctl[s].part;
-            if (part < 0) break;
-            const unsigned p = (unsigned)part;
-            const PartInfo pi = S.ctl[s].pi;
+            const int4 c0 = *reinterpret_cast<const int4 *>(&S.ctl[s].part);
+            if (c0.x < 0) break;
+            const unsigned p = (unsigned)c0.x;
+            const int f = c0.y, q = S.ctl[s].q;
             mbar_wait(&S.aggbar[s], ph);
-            uint32_t wt = lane < kConsumerWarps ? S.warptot[s][lane] : 0u;
+            const uint32_t wt = lane < kConsumerWarps ? S.warptot[s][lane] : 0u;
             const uint64_t agg = __reduce_add_sync(0xffffffffu, wt);
-            if (WST) {                               // exclusive prefix over the 8 tile warps
-                const uint32_t winc = warp_inclusive_scan(wt, lane);
-                if (lane < kConsumerWarps) S.wbase[s][lane] = winc - wt;
-                __syncwarp();
-            }
             uint64_t excl = 0;                      // U64 words of this frame before this partition
-            if (pi.q == 0) {
+            if (q == 0) {
                 if (lane == 0) st_relaxed_u64(P.desc + p, desc_make(kDescPrefix, agg));
             } else {
                 if (lane == 0) st_relaxed_u64(P.desc + p, desc_make(kDescAggregate, agg));
-#ifdef DBDE_EXP_SKIP_LOOKBACK      // profiling-only variant (WRONG output): isolates the pipeline from the scan chain
-                excl = (uint64_t)pi.q * 700;
-#else
-                excl = lookback_exclusive(P.desc, p, p - (unsigned)pi.q, lane);
-#endif
+                excl = lookback_exclusive(P.desc, p, p - (unsigned)q, lane);
                 if (lane == 0) st_relaxed_u64(P.desc + p, desc_make(kDescPrefix, excl + agg));
             }
             const size_t fixed = 32 + 2 * (size_t)g.wh;     // frame header + lengths + planes
-            uint8_t *frame = P.out + (size_t)pi.f * P.slot_stride;
+            uint8_t *frame = P.out + (size_t)f * P.slot_stride;
             if (lane == 0) {
                 S.base[s].frame = frame;
-                S.base[s].payload = frame + fixed + 8 * excl;
+                *reinterpret_cast<uint2 *>(&S.base[s].excl) = make_uint2((uint32_t)excl, (uint32_t)agg);
                 mbar_arrive(&S.basebar[s]);
             }
-            if (pi.q == g.ppf - 1) {
+            if (q == g.ppf - 1) {
                 // last partition of the frame: the fixed fields (dbde_util.cpp:141-146,182-188,191)
                 const uint32_t n64 = (uint32_t)(excl + agg);
-                const uint64_t index = P.first_index + (uint64_t)pi.f;
+                const uint64_t index = P.first_index + (uint64_t)f;
                 uint32_t b;      // lane i writes one byte of {I32 2 | U64 index | F64 0.0 | I32 wh} {I32 wh} {I32 n64}
                 uint8_t *dst;
                 if (lane < 4) { b = (2u >> (8 * lane)) & 0xff; dst = frame + lane; }
@@ -176,8 +222,8 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
                 else { b = (n64 >> (8 * (lane - 28))) & 0xff; dst = frame + 28 + 2 * (size_t)g.wh + (lane - 28); }
                 *dst = (uint8_t)b;
                 if (lane == 0) {
-                    P.frame_offsets[pi.f] = (uint64_t)pi.f * P.slot_stride;
-                    P.frame_sizes[pi.f] = fixed + 8ull * n64;
+                    P.frame_offsets[f] = (uint64_t)f * P.slot_stride;
+                    P.frame_sizes[f] = fixed + 8ull * n64;
                 }
             }
         }
@@ -190,98 +236,59 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
             sb = tid / g.w;
             stx = tid - sb * g.w;
         }
-        // deferred partition: its depth/min stay in registers until its addresses are known
-        int d_s = -1, d_k = 0, d_tfirst = 0;
-        uint32_t d_mn = 0, d_ph = 0, d_wtot = 0;
-        bool d_valid = false;
+        const uint32_t toff = (uint32_t)(sb * 8) * (uint32_t)g.pitch + (uint32_t)stx * 8u;   // my tile inside a stage
+        const size_t fixed = 32 + 2 * (size_t)g.wh;
+        // deferred partition (iteration it-1): its depth/min stay in registers until its addresses
+        // are known.  d_km = depth | min << 8 | valid << 16.
+        uint32_t d_km = 0;
+        int d_tfirst = 0;
 
-        // payload staging address of U64 word `a` (swizzled against bank conflicts).
-        //   !WST: a = word index inside the partition, staged linearly from the stage base
-        //    WST: a = word index inside this WARP's payload; word (32*row + col) lives where the
-        //         warp's pixel row `row`, column `col` was (wb = the warp's first pixel byte)
-        auto word_ptr = [&](uint8_t *wb, uint32_t a) -> uint8_t * {
-            if (WST) {
-                const uint32_t x = swz(a);
-                return wb + (size_t)(x >> 5) * g.pitch + 8u * (x & 31u);
-            }
-            return wb + swz_bytes(8u * a);
-        };
-        // copy `n` staged words to global memory at `dst`, spread over `nthr` threads (rank `me`)
-        auto copy_out = [&](uint8_t *wb, uint8_t *dst, uint32_t n, uint32_t me, uint32_t nthr) {
-            const uintptr_t ga = (uintptr_t)dst;
-            if ((ga & 7) == 0) {
-                // 16-byte stores over the aligned middle, one 8-byte word at either end if needed
-                const uint32_t head = (uint32_t)((ga >> 3) & 1);
-                if (head && me == 0 && n) st_stream_u64(dst, *reinterpret_cast<const uint64_t *>(word_ptr(wb, 0)));
-                const uint32_t npair = n > head ? (n - head) >> 1 : 0u;
-                for (uint32_t i = me; i < npair; i += nthr) {
-                    const uint32_t a = head + 2 * i;
-                    st_stream_v2u64(dst + 8 * (size_t)a, *reinterpret_cast<const uint64_t *>(word_ptr(wb, a)),
-                                    *reinterpret_cast<const uint64_t *>(word_ptr(wb, a + 1)));
-                }
-                const uint32_t done = head + 2 * npair;
-                if (done < n && me == 1)
-                    st_stream_u64(dst + 8 * (size_t)done, *reinterpret_cast<const uint64_t *>(word_ptr(wb, done)));
-            } else if ((ga & 3) == 0) {
-                for (uint32_t i = me; i < 2 * n; i += nthr)
-                    st_stream_u32(dst + 4 * (size_t)i, *reinterpret_cast<const uint32_t *>(word_ptr(wb, i >> 1) + 4 * (i & 1)));
-            } else {
-                for (uint32_t i = me; i < 8 * n; i += nthr) dst[i] = word_ptr(wb, i >> 3)[i & 7];
-            }
-        };
-
-        auto flush_deferred = [&]() {
-            uint8_t *stage = stages + (size_t)d_s * g.stage_bytes;
-            mbar_wait(&S.basebar[d_s], d_ph);
-            uint8_t *frame = S.base[d_s].frame;
-            uint8_t *payload = S.base[d_s].payload;
+        auto flush_deferred = [&](unsigned dit) {
+            const int ds = dit % kEncStages;
+            const uint8_t *stage = stages + (size_t)ds * g.stage_bytes;
+            mbar_wait(&S.basebar[ds], (dit / kEncStages) & 1);
+            const uint4 b = *reinterpret_cast<const uint4 *>(&S.base[ds]);
+            uint8_t *frame = reinterpret_cast<uint8_t *>(((uint64_t)b.y << 32) | b.x);
             // ---- depth and minimum planes (dbde_util.cpp:156-157)
-            if (d_valid) {
-                frame[24 + d_tfirst + tid] = (uint8_t)d_k;
-                frame[28 + (size_t)g.wh + d_tfirst + tid] = (uint8_t)d_mn;
+            if (d_km >> 16) {
+                uint8_t *pl = frame + d_tfirst + tid;
+                pl[24] = (uint8_t)d_km;
+                pl[28 + (size_t)g.wh] = (uint8_t)(d_km >> 8);
             }
-            // ---- coalesced copy-out
-            if (WST) {      // this warp's words, by this warp
-                uint8_t *wb = stage + (size_t)(sb * 8) * g.pitch + 8 * (stx - lane);
-                copy_out(wb, payload + 8 * (size_t)S.wbase[d_s][warp], d_wtot, (uint32_t)lane, 32u);
-            } else {        // the partition's words, by all tile warps
-                uint32_t total = 0;
-#pragma unroll
-                for (int wv = 0; wv < kConsumerWarps; wv++) total += S.warptot[d_s][wv];
-                copy_out(stage, payload, total, (uint32_t)tid, (uint32_t)kTilesPerPart);
-            }
+            // ---- coalesced copy-out of the partition's words, by all tile warps
+            enc_copy_out(stage, frame + fixed + 8 * (size_t)b.z, b.w, (uint32_t)tid);
             fence_proxy_async();        // my generic accesses to the stage precede the next TMA fill
             __syncwarp();
-            if (lane == 0) mbar_arrive(&S.empty[d_s]);
-            d_s = -1;
+            if (lane == 0) mbar_arrive(&S.empty[ds]);
         };
 
-        for (unsigned it = 0;; it++) {
+        unsigned it = 0;
+        for (;; it++) {
             const int s = it % kEncStages;
             const uint32_t ph = (it / kEncStages) & 1;
             mbar_wait(&S.full[s], ph);
-            const int part = S.ctl[s].part;
-            if (part < 0) break;
-            const PartInfo pi = S.ctl[s].pi;
+            const int4 c0 = *reinterpret_cast<const int4 *>(&S.ctl[s].part);   // part, f, tfirst, nt
+            if (c0.x < 0) break;
             uint8_t *stage = stages + (size_t)s * g.stage_bytes;
-            const bool valid = tid < pi.nt;
-            const int asb = valid ? sb : 0, astx = valid ? stx : 0;   // idle lanes read (and discard) tile 0
+            const bool valid = tid < c0.w;
 
             // ---- stage (1)->registers: 8 rows x 8 bytes
             uint32_t px[16];
             if (FAST) {
-                const uint8_t *base = stage + (size_t)(asb * 8) * g.pitch + astx * 8;
+                const uint8_t *base = stage + (valid ? toff : 0u);     // idle lanes read (and discard) tile 0
 #pragma unroll
                 for (int r = 0; r < 8; r++) {
-                    uint2 v = *reinterpret_cast<const uint2 *>(base + (size_t)r * g.pitch);
+                    const uint2 v = *reinterpret_cast<const uint2 *>(base);
+                    base += g.pitch;
                     px[2 * r] = v.x;
                     px[2 * r + 1] = v.y;
                 }
             } else {
                 // clamp-to-edge padding (dbde_util.cpp:105-135): rows past H repeat the last valid
                 // row, columns past W repeat the last valid pixel of the row
-                const int rows_valid = min(8, g.H - 8 * (pi.y0 + sb));
-                const int ncol = min(8, g.W - 8 * (pi.tx0 + stx));
+                const int y0 = S.ctl[s].y0, tx0 = S.ctl[s].tx0;
+                const int rows_valid = min(8, g.H - 8 * (y0 + sb));
+                const int ncol = min(8, g.W - 8 * (tx0 + stx));
 #pragma unroll
                 for (int r = 0; r < 8; r++) {
                     uint2 v = make_uint2(0u, 0u);
@@ -306,37 +313,24 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
             if (!valid) { k = 0; mn = 0; }
             // ---- stage (3a): depth sums -> scan warp
             const uint32_t incl = warp_inclusive_scan((uint32_t)k, lane);
-            const uint32_t wtot = __shfl_sync(0xffffffffu, incl, 31);
             if (lane == 31) {
                 S.warptot[s][warp] = incl;
                 mbar_arrive(&S.aggbar[s]);
             }
-            uint32_t off = incl - (uint32_t)k;          // WST: word offset inside the warp's payload
-            uint8_t *wb;
-            if (WST) {
-                // the shuffles above already converged the warp: every lane's pixels are in registers,
-                // so the warp's own slice of the stage is dead and becomes its payload staging
-                wb = stage + (size_t)(sb * 8) * g.pitch + 8 * (stx - lane);
-            } else {
-                // every tile of this partition is in registers (its stage may be overwritten) and every
-                // payload word of the deferred partition has been staged (it may be copied out)
-                bar_consumers();
-#pragma unroll
-                for (int wv = 0; wv < kConsumerWarps; wv++) {
-                    const uint32_t t = S.warptot[s][wv];
-                    if (wv < warp) off += t;
-                }
-                wb = stage;
-            }
-            // ---- stage (4): pack (p - min) into k U64 words, staged (swizzled) in the dead pixel bytes
+            // every tile of this partition is in registers (its stage may be overwritten) and every
+            // payload word of the deferred partition has been staged (it may be copied out)
+            bar_consumers();
+            // word offset of my tile inside the partition: lower warps' totals (REDUX) + my warp's prefix
+            const uint32_t wt = lane < warp ? S.warptot[s][lane & (kConsumerWarps - 1)] : 0u;
+            const uint32_t off = __reduce_add_sync(0xffffffffu, wt) + incl - (uint32_t)k;
+            // ---- stage (4): pack (p - min) into k U64 words, staged linearly in the dead pixel bytes
             if (k > 0) {
                 const uint32_t c1 = (1u << k) - 256u, c2 = (1u << (2 * k)) - 65536u;
                 uint32_t q[16];
 #pragma unroll
                 for (int i = 0; i < 16; i++) q[i] = squeeze4(px[i], c1, c2);
-                auto store = [&](int n, uint32_t lo, uint32_t hi) {
-                    *reinterpret_cast<uint2 *>(word_ptr(wb, off + (uint32_t)n)) = make_uint2(lo, hi);
-                };
+                uint2 *wp = reinterpret_cast<uint2 *>(stage + 8 * off);
+                auto store = [&](int n, uint32_t lo, uint32_t hi) { wp[n] = make_uint2(lo, hi); };
                 switch (k) {
                     case 1: concat_fields<1>(q, store); break;
                     case 2: concat_fields<2>(q, store); break;
@@ -345,16 +339,16 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
                     case 5: concat_fields<5>(q, store); break;
                     case 6: concat_fields<6>(q, store); break;
                     case 7: concat_fields<7>(q, store); break;
-                    default: concat_fields<8>(q, store); break;
+                    default: enc_store_depth8(q, stage + 8 * off, off); break;   // squeeze4 is the identity at depth 8
                 }
             }
-            if (WST) __syncwarp();      // the warp's payload is staged before any lane copies it out later
-            if (d_s >= 0) flush_deferred();
-            d_s = s; d_ph = ph; d_k = k; d_mn = mn; d_tfirst = pi.tfirst; d_valid = valid; d_wtot = wtot;
+            if (it > 0) flush_deferred(it - 1);
+            d_km = (uint32_t)k | (mn << 8) | ((uint32_t)valid << 16);
+            d_tfirst = c0.z;
         }
-        if (d_s >= 0) {
-            if (!WST) bar_consumers();  // the last partition's payload is fully staged
-            flush_deferred();
+        if (it > 0) {
+            bar_consumers();            // the last partition's payload is fully staged
+            flush_deferred(it - 1);
         }
     }
 }
@@ -365,13 +359,7 @@ size_t enc_smem_bytes(const PartGeom &g) {
 
 cudaError_t launch_encode(const EncParams &P, bool fast, int num_sms, cudaStream_t stream) {
     const size_t smem = enc_smem_bytes(P.g);
-    // warp-private staging needs whole warps inside one band: every partition's ntx % 32 == 0
-    // Measured on B200 (micro-2048): CTA-wide staging 1.18 ms vs warp-private 1.24 ms per 1000 frames
-    // -- the barrier it removes is hidden by the other resident CTAs while its address math is not --
-    // so it stays an opt-in experiment (DBDE_B200_WST=1).
-    static const bool want_wst = getenv("DBDE_B200_WST") && atoi(getenv("DBDE_B200_WST")) != 0;
-    const bool wst = want_wst && fast && (P.g.w % 32 == 0);
-    auto kern = !fast ? dbde_encode_kernel<false, false> : (wst ? dbde_encode_kernel<true, true> : dbde_encode_kernel<true, false>);
+    auto kern = fast ? dbde_encode_kernel<true> : dbde_encode_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 0;
