@@ -5,6 +5,7 @@
 #include "dbde_kernels.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -27,20 +28,22 @@ static int cuda_fail(cudaError_t e, const char *where) {
         if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
     } while (0)
 
-constexpr int kHostSlots = 3;
+constexpr int kMaxHostSlots = 8;
+constexpr int kDefaultHostSlots = 3;
 
 struct HostSlot {
     cudaStream_t st = nullptr;
     cudaEvent_t ev = nullptr;
     uint8_t *d_a = nullptr;      // encode: frames   | decode: stream bytes
-    uint8_t *d_b = nullptr;      // encode: records  | decode: frames
+    uint8_t *d_b = nullptr;      // encode: records in their slots | decode: frames
+    uint8_t *d_c = nullptr;      // encode: records back to back (compacted on the device)
     uint64_t *d_off = nullptr;
     uint64_t *d_size = nullptr;
     uint32_t *d_status = nullptr;
     uint64_t *d_index = nullptr;
     uint64_t *h_off = nullptr;   // pinned
     uint64_t *h_size = nullptr;  // pinned
-    size_t cap_a = 0, cap_b = 0;
+    size_t cap_a = 0, cap_b = 0, cap_c = 0;
     int cap_n = 0;
     int n = 0, first = 0;
 };
@@ -52,8 +55,9 @@ struct dbde_b200_ctx {
     size_t enc_scratch_bytes = 0;
     void *dec_scratch = nullptr;
     size_t dec_scratch_bytes = 0;
-    HostSlot slots[kHostSlots];
-    int chunk_frames = 0;
+    HostSlot slots[kMaxHostSlots];
+    int nslots = kDefaultHostSlots;   // staging slots in flight (DBDE_B200_SLOTS)
+    int chunk_frames = 0;             // frames per chunk, 0 = auto (DBDE_B200_CHUNK_FRAMES)
     uint64_t launches = 0;
 };
 
@@ -122,6 +126,14 @@ extern "C" int dbde_b200_create(int device, dbde_b200_ctx **out) {
     dbde_b200_ctx *c = new dbde_b200_ctx();
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
+    if (const char *e = getenv("DBDE_B200_SLOTS")) {
+        const int n = atoi(e);
+        if (n >= 2 && n <= kMaxHostSlots) c->nslots = n;
+    }
+    if (const char *e = getenv("DBDE_B200_CHUNK_FRAMES")) {
+        const int n = atoi(e);
+        if (n > 0) c->chunk_frames = n;
+    }
     *out = c;
     return 0;
 }
@@ -129,6 +141,7 @@ extern "C" int dbde_b200_create(int device, dbde_b200_ctx **out) {
 static void free_slot(HostSlot &s) {
     if (s.d_a) cudaFree(s.d_a);
     if (s.d_b) cudaFree(s.d_b);
+    if (s.d_c) cudaFree(s.d_c);
     if (s.d_off) cudaFree(s.d_off);
     if (s.d_size) cudaFree(s.d_size);
     if (s.h_size) cudaFreeHost(s.h_size);
@@ -301,7 +314,7 @@ static int default_chunk(const dbde_b200_ctx *c, int W, int H, int nframes) {
     return n;
 }
 
-static int ensure_slot(dbde_b200_ctx *c, HostSlot &s, size_t need_a, size_t need_b, int n) {
+static int ensure_slot(dbde_b200_ctx *c, HostSlot &s, size_t need_a, size_t need_b, size_t need_c, int n) {
     if (!s.st) CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
     if (!s.ev) CK(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
     if (s.cap_a < need_a) {
@@ -315,6 +328,12 @@ static int ensure_slot(dbde_b200_ctx *c, HostSlot &s, size_t need_a, size_t need
         s.d_b = nullptr;
         CK(cudaMalloc(&s.d_b, need_b));
         s.cap_b = need_b;
+    }
+    if (s.cap_c < need_c) {
+        if (s.d_c) CK(cudaFree(s.d_c));
+        s.d_c = nullptr;
+        CK(cudaMalloc(&s.d_c, need_c));
+        s.cap_c = need_c;
     }
     if (s.cap_n < n) {
         if (s.d_off) CK(cudaFree(s.d_off));
@@ -349,48 +368,33 @@ extern "C" int dbde_b200_encode_host(dbde_b200_ctx *c, const uint8_t *frames_hos
     const int chunk = default_chunk(c, W, H, nframes);
     const size_t delta = payload_align_delta(W, H);
     const size_t need_a = px * chunk + 32, need_b = dbde_b200_stream_bound(W, H, chunk) + 32;
-    for (auto &s : c->slots) {
-        int rc = ensure_slot(c, s, need_a, need_b, chunk);
+    for (int i = 0; i < c->nslots; i++) {
+        int rc = ensure_slot(c, c->slots[i], need_a, need_b, need_b, chunk);
         if (rc) return rc;
     }
     const int nchunks = (nframes + chunk - 1) / chunk;
     const size_t stride = dbde_b200_slot_stride(W, H);
     size_t out_pos = 0;
     int rc_all = 0;
-    // finish(): wait for a chunk's kernel, learn the record sizes, and queue the D2H copies that
-    // lay the records back to back at the running offset (the host-side concatenation).  Large
-    // records go slot by slot; small ones come back as one block and are compacted on the host.
-    std::vector<uint8_t> small;
+    // finish(): wait for a chunk's kernels, learn the record sizes, and queue ONE D2H copy of the
+    // chunk's records -- already laid back to back on the device -- to the running offset in
+    // out_host (the host-side concatenation across chunks).
     auto finish = [&](int ci) -> int {
-        HostSlot &s = c->slots[ci % kHostSlots];
+        HostSlot &s = c->slots[ci % c->nslots];
         CK(cudaEventSynchronize(s.ev));
         uint64_t total = 0;
-        for (int i = 0; i < s.n; i++) total += s.h_size[i];
-        if (out_pos + total > out_capacity) return fail(DBDE_B200_E_CAPACITY, "encode_host: out_capacity too small");
-        if (stride >= 65536) {
-            size_t pos = out_pos;
-            for (int i = 0; i < s.n; i++) {
-                CK(cudaMemcpyAsync(out_host + pos, s.d_b + delta + (size_t)i * stride, s.h_size[i], cudaMemcpyDeviceToHost, s.st));
-                frame_offsets_host[s.first + i] = pos;
-                pos += s.h_size[i];
-            }
-        } else {
-            small.resize(stride * (size_t)s.n);
-            CK(cudaMemcpyAsync(small.data(), s.d_b + delta, stride * (size_t)s.n, cudaMemcpyDeviceToHost, s.st));
-            CK(cudaStreamSynchronize(s.st));
-            size_t pos = out_pos;
-            for (int i = 0; i < s.n; i++) {
-                memcpy(out_host + pos, small.data() + (size_t)i * stride, s.h_size[i]);
-                frame_offsets_host[s.first + i] = pos;
-                pos += s.h_size[i];
-            }
+        for (int i = 0; i < s.n; i++) {
+            frame_offsets_host[s.first + i] = out_pos + total;
+            total += s.h_size[i];
         }
+        if (out_pos + total > out_capacity) return fail(DBDE_B200_E_CAPACITY, "encode_host: out_capacity too small");
+        CK(cudaMemcpyAsync(out_host + out_pos, s.d_c, total, cudaMemcpyDeviceToHost, s.st));
         out_pos += total;
         return 0;
     };
     int pending = -1;
     for (int ci = 0; ci < nchunks && !rc_all; ci++) {
-        HostSlot &s = c->slots[ci % kHostSlots];
+        HostSlot &s = c->slots[ci % c->nslots];
         CK(cudaStreamSynchronize(s.st));            // the slot's previous chunk has fully drained
         s.first = ci * chunk;
         s.n = nframes - s.first < chunk ? nframes - s.first : chunk;
@@ -399,6 +403,8 @@ extern "C" int dbde_b200_encode_host(dbde_b200_ctx *c, const uint8_t *frames_hos
                                          need_b - 32, stride, s.d_off, s.d_size, s.st);
         if (rc_all) break;
         CK(cudaMemcpyAsync(s.h_size, s.d_size, 8 * (size_t)s.n, cudaMemcpyDeviceToHost, s.st));
+        CK(launch_compact(s.d_b + delta, stride, s.d_size, s.n, s.d_c, s.st));
+        c->launches += 1;
         CK(cudaEventRecord(s.ev, s.st));
         if (pending >= 0) rc_all = finish(pending);
         pending = ci;
@@ -437,15 +443,15 @@ extern "C" int dbde_b200_decode_host(dbde_b200_ctx *c, const uint8_t *stream_hos
     }
     need_a += 64;
     const size_t need_b = px * chunk + 32;
-    for (auto &s : c->slots) {
-        int rc = ensure_slot(c, s, need_a, need_b, chunk);
+    for (int i = 0; i < c->nslots; i++) {
+        int rc = ensure_slot(c, c->slots[i], need_a, need_b, 0, chunk);
         if (rc) return rc;
     }
     // finish(): wait for a chunk's status words, then queue the D2H of its accepted frames.  A
     // rejected frame must leave the caller's image untouched (dbde_util.cpp:296-303), so pixels
     // come back as maximal runs of accepted frames.
     auto finish = [&](int ci) -> int {
-        HostSlot &s = c->slots[ci % kHostSlots];
+        HostSlot &s = c->slots[ci % c->nslots];
         CK(cudaEventSynchronize(s.ev));
         int run0 = 0;
         for (int i = 0; i <= s.n; i++) {
@@ -461,7 +467,7 @@ extern "C" int dbde_b200_decode_host(dbde_b200_ctx *c, const uint8_t *stream_hos
     };
     int pending = -1, rc_all = 0;
     for (int ci = 0; ci < nchunks && !rc_all; ci++) {
-        HostSlot &s = c->slots[ci % kHostSlots];
+        HostSlot &s = c->slots[ci % c->nslots];
         CK(cudaStreamSynchronize(s.st));
         s.first = ci * chunk;
         s.n = nframes - s.first < chunk ? nframes - s.first : chunk;

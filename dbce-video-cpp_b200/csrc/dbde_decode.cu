@@ -152,11 +152,14 @@ __global__ void __launch_bounds__(256) dbde_decode_scan_kernel(const DecParams P
 }
 
 // ------------------------------------------------------------------ main kernel
-struct DecCtl {
+struct alignas(16) DecCtl {
     int part;                  // -1 = no more work
     int skip;                  // frame was rejected by the scan: leave the image untouched
-    PartInfo pi;               // geometry of the partition (computed once, by the producer)
+    int f;                     // frame within the batch
+    int nt;                    // tiles in this partition
     uint32_t pres, kres, mres; // residual byte offsets of payload / depth / min inside their hulls
+    uint32_t pixoff;           // byte offset of the partition's first pixel inside its frame
+    int y0, tx0, pad0, pad1;   // first band / first tile column (generic path)
     uint32_t wbase[kConsumerWarps];   // word offset of each tile warp inside the partition's payload
 };
 struct DecSmem {
@@ -251,8 +254,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecPa
             }
             if (status != 0) {
                 if (lane == 0) {
-                    S.ctl[s].part = (int)p;
-                    S.ctl[s].skip = 1;
+                    *reinterpret_cast<int2 *>(&S.ctl[s].part) = make_int2((int)p, 1);
                     mbar_arrive(&S.full[s]);
                 }
                 continue;
@@ -274,9 +276,14 @@ __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecPa
             const uint32_t len = nbytes ? (uint32_t)(a1 - a0) : 0u;
             const uint32_t res = (uint32_t)((uintptr_t)src - a0);
             if (lane < kConsumerWarps) S.ctl[s].wbase[lane] = v - v0;
-            if (lane == 0) { S.ctl[s].pres = res; S.ctl[s].part = (int)p; S.ctl[s].skip = 0; S.ctl[s].pi = pi; }
-            if (lane == 1) S.ctl[s].kres = res;
-            if (lane == 2) S.ctl[s].mres = res;
+            // lanes 0..2 hold the three residuals: gather them so lane 0 writes the block with two 16-byte stores
+            const uint32_t kres = __shfl_sync(0xffffffffu, res, 1), mres = __shfl_sync(0xffffffffu, res, 2);
+            if (lane == 0) {
+                *reinterpret_cast<int4 *>(&S.ctl[s].part) = make_int4((int)p, 0, pi.f, pi.nt);
+                *reinterpret_cast<uint4 *>(&S.ctl[s].pres) =
+                    make_uint4(res, kres, mres, (uint32_t)(8 * pi.y0) * (uint32_t)g.W + 8u * (uint32_t)pi.tx0);
+                *reinterpret_cast<int2 *>(&S.ctl[s].y0) = make_int2(pi.y0, pi.tx0);
+            }
             const uint32_t total = __reduce_add_sync(0xffffffffu, lane < 3 ? len : 0u);
             __syncwarp();
             if (lane == 0) mbar_arrive_expect_tx(&S.full[s], total);
@@ -290,26 +297,28 @@ __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecPa
             sb = tid / g.w;
             stx = tid - sb * g.w;
         }
+        const uint32_t toff = (uint32_t)(8 * sb) * (uint32_t)g.W + 8u * (uint32_t)stx;   // my tile inside a partition's pixels
+        const size_t rowstride = (size_t)g.W;
         for (unsigned it = 0;; it++) {
             const int s = it % kDecStages;
             const uint32_t ph = (it / kDecStages) & 1;
             mbar_wait(&S.full[s], ph);
-            const int part = S.ctl[s].part;
-            if (part < 0) break;
-            if (S.ctl[s].skip) {
+            const int4 c0 = *reinterpret_cast<const int4 *>(&S.ctl[s].part);      // part, skip, f, nt
+            if (c0.x < 0) break;
+            if (c0.y) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&S.empty[s]);
                 continue;
             }
-            const PartInfo pi = S.ctl[s].pi;
+            const uint4 c1 = *reinterpret_cast<const uint4 *>(&S.ctl[s].pres);    // pres, kres, mres, pixoff
             const uint8_t *stage = stages + (size_t)s * kDecStageBytes;
-            const bool valid = tid < pi.nt;
-            const uint32_t pres = S.ctl[s].pres;
+            const bool valid = tid < c0.w;
+            const uint32_t pres = c1.x;
             int k = 0;
             uint32_t mn = 0;
             if (valid) {
-                k = stage[kDecPayloadBytes + S.ctl[s].kres + tid];
-                mn = stage[kDecPayloadBytes + kDecPlaneBytes + S.ctl[s].mres + tid];
+                k = stage[kDecPayloadBytes + c1.y + tid];
+                mn = stage[kDecPayloadBytes + kDecPlaneBytes + c1.z + tid];
             }
             const uint32_t incl = warp_inclusive_scan((uint32_t)k, lane);
             const uint32_t woff = S.ctl[s].wbase[warp] + incl - (uint32_t)k;
@@ -318,8 +327,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecPa
             if (k > 0) {
                 uint32_t q[16];
                 const uint8_t *pay = stage + pres + 8 * (size_t)woff;
-                if ((pres & 7u) == 0) load_split_any<8>(k, pay, q);
-                else if ((pres & 3u) == 0) load_split_any<4>(k, pay, q);
+                if ((pres & 7u) == 0) load_split_any<8>(k, pay, q);     // the usual case: records on 8-byte boundaries
                 else load_split_any<1>(k, pay, q);
                 const uint32_t c1n = 256u - (1u << k), c2n = 65536u - (1u << (2 * k));
                 const uint32_t kmask2 = ((1u << k) - 1u) * 0x00010001u;
@@ -333,24 +341,23 @@ __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecPa
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.empty[s]);       // payload is in registers: free the stage early
 
-            uint8_t *fptr = P.frames + (size_t)pi.f * fbytes;
+            uint8_t *rp = P.frames + (size_t)c0.z * fbytes + (c1.w + toff);
             if (FAST) {
                 // no edges, 8-byte aligned rows: lane t stores 8 bytes of each row, a warp 256 contiguous bytes
                 if (valid) {
-                    uint8_t *base = fptr + (size_t)(8 * (pi.y0 + sb)) * g.W + 8 * (pi.tx0 + stx);
 #pragma unroll
-                    for (int r = 0; r < 8; r++)
-                        st_stream_u64(base + (size_t)r * g.W, ((uint64_t)px[2 * r + 1] << 32) | px[2 * r]);
+                    for (int r = 0; r < 8; r++) {
+                        st_stream_u64(rp, ((uint64_t)px[2 * r + 1] << 32) | px[2 * r]);
+                        rp += rowstride;
+                    }
                 }
             } else if (valid) {
                 // crop the padding (dbde_util.cpp:281-289): only rows < H and columns < W are written
-                const int rows_valid = min(8, g.H - 8 * (pi.y0 + sb));
-                const int ncol = min(8, g.W - 8 * (pi.tx0 + stx));
-                uint8_t *base = fptr + (size_t)(8 * (pi.y0 + sb)) * g.W + 8 * (pi.tx0 + stx);
+                const int rows_valid = min(8, g.H - 8 * (S.ctl[s].y0 + sb));
+                const int ncol = min(8, g.W - 8 * (S.ctl[s].tx0 + stx));
 #pragma unroll
                 for (int r = 0; r < 8; r++) {
                     if (r < rows_valid) {
-                        uint8_t *rp = base + (size_t)r * g.W;
                         if (ncol == 8 && (((uintptr_t)rp) & 7) == 0) {
                             *reinterpret_cast<uint2 *>(rp) = make_uint2(px[2 * r], px[2 * r + 1]);
                         } else {
@@ -358,6 +365,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecPa
                             for (int c = 0; c < ncol; c++) rp[c] = (uint8_t)(x >> (8 * c));
                         }
                     }
+                    rp += rowstride;
                 }
             }
         }

@@ -353,6 +353,40 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
     }
 }
 
+// ------------------------------------------------------------------ record compaction
+// Lays the records of a batch back to back on the device (slot f -> dst + sum of the sizes before f),
+// so the host path brings a chunk home with ONE large D2H copy instead of one per record: small
+// copies cost PCIe duplex throughput (measured 70 vs 97 GB/s with 1.6 MB vs 64 MiB pieces).
+// grid = (blocks per record, records).  HBM traffic: 2 x record bytes, ~1 % of the PCIe time.
+__global__ void __launch_bounds__(256) dbde_compact_kernel(const uint8_t *slots, uint64_t slot_stride,
+                                                           const uint64_t *sizes, int n, uint8_t *dst) {
+    const int f = blockIdx.y;
+    uint64_t before = 0;
+    for (int i = 0; i < f; i++) before += sizes[i];           // n is a chunk (tens of records)
+    const uint64_t bytes = sizes[f];
+    const uint8_t *src = slots + (uint64_t)f * slot_stride;
+    uint8_t *d = dst + before;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (uint64_t)gridDim.x * blockDim.x;
+    if ((((uintptr_t)src | (uintptr_t)d) & 7) == 0) {
+        const uint64_t *s8 = reinterpret_cast<const uint64_t *>(src);
+        const uint64_t n8 = bytes >> 3;
+        for (uint64_t i = t; i < n8; i += nt) st_stream_u64(d + 8 * i, __ldcs(s8 + i));
+        for (uint64_t i = (n8 << 3) + t; i < bytes; i += nt) d[i] = src[i];
+    } else {
+        for (uint64_t i = t; i < bytes; i += nt) d[i] = src[i];
+    }
+}
+
+cudaError_t launch_compact(const uint8_t *slots, uint64_t slot_stride, const uint64_t *sizes, int n, uint8_t *dst,
+                           cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    unsigned bx = (unsigned)((slot_stride / 8 + 256 * 8 - 1) / (256 * 8));     // ~8 words per thread at worst-case size
+    if (bx < 1) bx = 1;
+    if (bx > 64) bx = 64;
+    dbde_compact_kernel<<<dim3(bx, (unsigned)n), 256, 0, stream>>>(slots, slot_stride, sizes, n, dst);
+    return cudaGetLastError();
+}
+
 size_t enc_smem_bytes(const PartGeom &g) {
     return ((sizeof(EncSmem) + 127) & ~(size_t)127) + (size_t)kEncStages * g.stage_bytes;
 }

@@ -44,6 +44,8 @@ enum : uint32_t {
 size_t enc_smem_bytes(const PartGeom &g);
 size_t dec_smem_bytes(const PartGeom &g);
 cudaError_t launch_encode(const EncParams &P, bool fast, int num_sms, cudaStream_t stream);
+cudaError_t launch_compact(const uint8_t *slots, uint64_t slot_stride, const uint64_t *sizes, int n, uint8_t *dst,
+                           cudaStream_t stream);
 cudaError_t launch_decode_scan(const DecParams &P, cudaStream_t stream);
 cudaError_t launch_decode(const DecParams &P, bool fast, int num_sms, cudaStream_t stream);
 
