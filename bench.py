@@ -332,7 +332,9 @@ def run_ours(a):
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(dom, {}).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))      # ncu dram__bytes_read+write per launch, captured for ONE workload
+            if tj.get("workload") == {"kind": a.kind, "width": Ww, "height": Hh, "frames": N}:
+                traffic = tj.get(dom, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": "dbde_%s_kernel" % dom, "achieved": enc_gbs if dom == "encode" else dec_gbs,
