@@ -61,17 +61,26 @@ __device__ __forceinline__ void enc_copy_out(const uint8_t *stage, uint8_t *dst,
             if (n && me == 0) st_stream_u64(dst, *reinterpret_cast<const uint64_t *>(stage));
             return;
         }
-        const uint32_t npair = (n - head) >> 1;
+        const uint32_t npair = (n - head) >> 1;                 // <= 1024: at most four rounds of 256 threads
         const uint8_t *sp = stage + 8 * head + 16 * me;
         uint8_t *dp = dst + 8 * head + 16 * me;
         if (head == 0) {
-            for (uint32_t i = me; i < npair; i += kTilesPerPart, sp += 16 * kTilesPerPart, dp += 16 * kTilesPerPart)
-                st_stream_v4u32(dp, *reinterpret_cast<const uint4 *>(sp));
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (j * kTilesPerPart >= npair) break;
+                if (me + j * kTilesPerPart < npair)
+                    st_stream_v4u32(dp + 16 * kTilesPerPart * j, *reinterpret_cast<const uint4 *>(sp + 16 * kTilesPerPart * j));
+            }
         } else {
             if (me == 0) st_stream_u64(dst, *reinterpret_cast<const uint64_t *>(stage));
-            for (uint32_t i = me; i < npair; i += kTilesPerPart, sp += 16 * kTilesPerPart, dp += 16 * kTilesPerPart) {
-                const uint2 a = *reinterpret_cast<const uint2 *>(sp), b = *reinterpret_cast<const uint2 *>(sp + 8);
-                st_stream_v4u32(dp, make_uint4(a.x, a.y, b.x, b.y));
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (j * kTilesPerPart >= npair) break;
+                if (me + j * kTilesPerPart < npair) {
+                    const uint2 a = *reinterpret_cast<const uint2 *>(sp + 16 * kTilesPerPart * j);
+                    const uint2 b = *reinterpret_cast<const uint2 *>(sp + 16 * kTilesPerPart * j + 8);
+                    st_stream_v4u32(dp + 16 * kTilesPerPart * j, make_uint4(a.x, a.y, b.x, b.y));
+                }
             }
         }
         const uint32_t done = head + 2 * npair;
@@ -102,7 +111,11 @@ __device__ __forceinline__ void enc_store_depth8(const uint32_t (&w)[16], uint8_
 }
 
 // FAST : 16-byte aligned rows, no partial tiles (W % 16 == 0, H % 8 == 0).
-template <bool FAST>
+// WIDE : FAST and w % 256 == 0 (2048-, 4096-pixel-wide frames): every partition is one full 256-tile
+//        band segment, so the smem pitch is the constant 2048 (immediate-offset row loads) and no
+//        lane is ever idle.
+constexpr int kWidePitch = 8 * kTilesPerPart;
+template <bool FAST, bool WIDE>
 __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     EncSmem &S = *reinterpret_cast<EncSmem *>(smem_raw);
@@ -270,11 +283,19 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
             const int4 c0 = *reinterpret_cast<const int4 *>(&S.ctl[s].part);   // part, f, tfirst, nt
             if (c0.x < 0) break;
             uint8_t *stage = stages + (size_t)s * g.stage_bytes;
-            const bool valid = tid < c0.w;
+            const bool valid = WIDE || tid < c0.w;
 
             // ---- stage (1)->registers: 8 rows x 8 bytes
             uint32_t px[16];
-            if (FAST) {
+            if (WIDE) {
+                const uint8_t *base = stage + 8 * tid;
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    const uint2 v = *reinterpret_cast<const uint2 *>(base + r * kWidePitch);
+                    px[2 * r] = v.x;
+                    px[2 * r + 1] = v.y;
+                }
+            } else if (FAST) {
                 const uint8_t *base = stage + (valid ? toff : 0u);     // idle lanes read (and discard) tile 0
 #pragma unroll
                 for (int r = 0; r < 8; r++) {
@@ -393,7 +414,8 @@ size_t enc_smem_bytes(const PartGeom &g) {
 
 cudaError_t launch_encode(const EncParams &P, bool fast, int num_sms, cudaStream_t stream) {
     const size_t smem = enc_smem_bytes(P.g);
-    auto kern = fast ? dbde_encode_kernel<true> : dbde_encode_kernel<false>;
+    const bool wide = fast && (P.g.w % kTilesPerPart == 0) && P.g.pitch == kWidePitch;
+    auto kern = wide ? dbde_encode_kernel<true, true> : (fast ? dbde_encode_kernel<true, false> : dbde_encode_kernel<false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 0;
