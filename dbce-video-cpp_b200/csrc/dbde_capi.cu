@@ -368,11 +368,12 @@ extern "C" int dbde_b200_encode_host(dbde_b200_ctx *c, const uint8_t *frames_hos
     const int chunk = default_chunk(c, W, H, nframes);
     const size_t delta = payload_align_delta(W, H);
     const size_t need_a = px * chunk + 32, need_b = dbde_b200_stream_bound(W, H, chunk) + 32;
-    for (int i = 0; i < c->nslots; i++) {
+    const int nchunks = (nframes + chunk - 1) / chunk;
+    const int ns = nchunks < c->nslots ? nchunks : c->nslots;      // a one-frame call sets up one slot
+    for (int i = 0; i < ns; i++) {
         int rc = ensure_slot(c, c->slots[i], need_a, need_b, need_b, chunk);
         if (rc) return rc;
     }
-    const int nchunks = (nframes + chunk - 1) / chunk;
     const size_t stride = dbde_b200_slot_stride(W, H);
     size_t out_pos = 0;
     int rc_all = 0;
@@ -380,7 +381,7 @@ extern "C" int dbde_b200_encode_host(dbde_b200_ctx *c, const uint8_t *frames_hos
     // chunk's records -- already laid back to back on the device -- to the running offset in
     // out_host (the host-side concatenation across chunks).
     auto finish = [&](int ci) -> int {
-        HostSlot &s = c->slots[ci % c->nslots];
+        HostSlot &s = c->slots[ci % ns];
         CK(cudaEventSynchronize(s.ev));
         uint64_t total = 0;
         for (int i = 0; i < s.n; i++) {
@@ -394,7 +395,7 @@ extern "C" int dbde_b200_encode_host(dbde_b200_ctx *c, const uint8_t *frames_hos
     };
     int pending = -1;
     for (int ci = 0; ci < nchunks && !rc_all; ci++) {
-        HostSlot &s = c->slots[ci % c->nslots];
+        HostSlot &s = c->slots[ci % ns];
         CK(cudaStreamSynchronize(s.st));            // the slot's previous chunk has fully drained
         s.first = ci * chunk;
         s.n = nframes - s.first < chunk ? nframes - s.first : chunk;
@@ -443,7 +444,8 @@ extern "C" int dbde_b200_decode_host(dbde_b200_ctx *c, const uint8_t *stream_hos
     }
     need_a += 64;
     const size_t need_b = px * chunk + 32;
-    for (int i = 0; i < c->nslots; i++) {
+    const int ns = nchunks < c->nslots ? nchunks : c->nslots;
+    for (int i = 0; i < ns; i++) {
         int rc = ensure_slot(c, c->slots[i], need_a, need_b, 0, chunk);
         if (rc) return rc;
     }
@@ -451,7 +453,7 @@ extern "C" int dbde_b200_decode_host(dbde_b200_ctx *c, const uint8_t *stream_hos
     // rejected frame must leave the caller's image untouched (dbde_util.cpp:296-303), so pixels
     // come back as maximal runs of accepted frames.
     auto finish = [&](int ci) -> int {
-        HostSlot &s = c->slots[ci % c->nslots];
+        HostSlot &s = c->slots[ci % ns];
         CK(cudaEventSynchronize(s.ev));
         int run0 = 0;
         for (int i = 0; i <= s.n; i++) {
@@ -467,7 +469,7 @@ extern "C" int dbde_b200_decode_host(dbde_b200_ctx *c, const uint8_t *stream_hos
     };
     int pending = -1, rc_all = 0;
     for (int ci = 0; ci < nchunks && !rc_all; ci++) {
-        HostSlot &s = c->slots[ci % c->nslots];
+        HostSlot &s = c->slots[ci % ns];
         CK(cudaStreamSynchronize(s.st));
         s.first = ci * chunk;
         s.n = nframes - s.first < chunk ? nframes - s.first : chunk;

@@ -311,3 +311,24 @@ def test_file_walker(dropin):
                 assert hdr == (2, 100 + i, 0) and (img == fr[i]).all()
         finally:
             os.unlink(path)
+
+
+def test_the_references_own_test_program_passes_against_this_library():
+    """dbde_util_test.cpp -- the reference's whole test main (example tiles incl. the
+    three partial-tile cases, the 8x16 known-answer test in both directions, the 2536x2048 noise
+    round trip, 1024 random single-tile round trips) -- linked against libdbde_b200.so instead of
+    dbde_util.o (oracle/Makefile `reftest`).  It must exit 0 and print exactly what the same program
+    linked against the unmodified reference prints, apart from its three rdtsc timing lines."""
+    import subprocess
+    d = os.path.join(os.path.dirname(os.path.abspath(oracle.__file__)), "_ref")
+    ours, ref = os.path.join(d, "dbde_test_b200"), os.path.join(d, "dbde_test_ref")
+    if not (os.path.exists(ours) and os.path.exists(ref)):
+        pytest.skip("oracle/_ref test programs not built (needs /root/reference at build time)")
+    a = subprocess.run([ours], capture_output=True, text=True, timeout=300)
+    b = subprocess.run([ref], capture_output=True, text=True, timeout=300)
+    assert b.returncode == 0, b.stdout[-2000:]
+    assert a.returncode == 0, a.stdout[-2000:] + a.stderr[-2000:]
+    la, lb = a.stdout.splitlines(), b.stdout.splitlines()
+    assert len(la) == len(lb) and len(la) > 10
+    assert la[:-3] == lb[:-3]
+    assert "!! 0 of 5193728" in a.stdout and "Failed iteration" not in a.stdout
