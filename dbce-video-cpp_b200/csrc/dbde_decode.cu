@@ -159,7 +159,7 @@ struct alignas(16) DecCtl {
     int nt;                    // tiles in this partition
     uint32_t pres, kres, mres; // residual byte offsets of payload / depth / min inside their hulls
     uint32_t pixoff;           // byte offset of the partition's first pixel inside its frame
-    int y0, tx0, pad0, pad1;   // first band / first tile column (generic path)
+    int y0, tx0, ntx, pad1;    // first band / first tile column / tile columns (generic path)
     uint32_t wbase[kConsumerWarps];   // word offset of each tile warp inside the partition's payload
 };
 struct DecSmem {
@@ -201,6 +201,47 @@ __device__ __forceinline__ void load_split_any(int k, const uint8_t *pay, uint32
         case 7: load_split<7, ALIGN>(pay, q); break;
         default: load_split<8, ALIGN>(pay, q); break;
     }
+}
+
+// ------------------------------------------------------------------ generic (unaligned / cropped) row stores
+// Bytes [s, e) of the little-endian 64-bit `w` go to q + s .. q + e; q is 8-byte aligned, 0 <= s <= e <= 8.
+// At most six naturally aligned stores (1-2-4 up to alignment, then 4-2-1 down).
+__device__ __forceinline__ void store_partial(uint8_t *q, uint64_t w, uint32_t s, uint32_t e) {
+    if ((s & 1u) && e - s >= 1u) { q[s] = (uint8_t)(w >> (8 * s)); s += 1; }
+    if ((s & 2u) && e - s >= 2u) { *reinterpret_cast<uint16_t *>(q + s) = (uint16_t)(w >> (8 * s)); s += 2; }
+    if ((s & 4u) && e - s >= 4u) { *reinterpret_cast<uint32_t *>(q + s) = (uint32_t)(w >> (8 * s)); s += 4; }
+    if (e - s >= 4u) { *reinterpret_cast<uint32_t *>(q + s) = (uint32_t)(w >> (8 * s)); s += 4; }
+    if (e - s >= 2u) { *reinterpret_cast<uint16_t *>(q + s) = (uint16_t)(w >> (8 * s)); s += 2; }
+    if (e - s >= 1u) q[s] = (uint8_t)(w >> (8 * s));
+}
+
+// One pixel row of a warp's tiles, any alignment, cropped to `ncol` columns (dbde_util.cpp:281-289).
+// Consecutive lanes of a band hold consecutive 8-byte pieces of the row, so every lane assembles the
+// ALIGNED 8-byte word its piece starts in -- the tail of its left neighbour (one shuffle) plus its own
+// head -- and stores it whole: a warp's row is one run of aligned 8-byte stores.  Only the ends of a
+// run (first/last lane of the warp, first/last tile of the row) are written with narrower stores.
+// `a` = row address & 7 is the same for every lane (bands are a multiple of 8 bytes apart).
+// All 32 lanes call this (the shuffle is warp-wide); `live` says whether this lane has a row to write.
+__device__ __forceinline__ void store_row_generic(uint8_t *rp, uint64_t x, int ncol, bool live, bool first_in_run,
+                                                  bool last_in_run) {
+    const uint64_t prev = __shfl_up_sync(0xffffffffu, x, 1);
+    if (!live) return;
+    const uint32_t a = (uint32_t)(uintptr_t)rp & 7u;
+    if (a == 0) {
+        if (ncol == 8) *reinterpret_cast<uint2 *>(rp) = make_uint2((uint32_t)x, (uint32_t)(x >> 32));
+        else store_partial(rp, x, 0u, (uint32_t)ncol);
+        return;
+    }
+    uint8_t *q = rp - a;
+    const uint32_t sh = 8u * a;
+    uint64_t w = x << sh;
+    if (!first_in_run) w |= prev >> (64u - sh);
+    const uint32_t s = first_in_run ? a : 0u;
+    const uint32_t e = min(8u, a + (uint32_t)ncol);
+    if (s == 0u && e == 8u) *reinterpret_cast<uint2 *>(q) = make_uint2((uint32_t)w, (uint32_t)(w >> 32));
+    else store_partial(q, w, s, e);
+    // my bytes past the word boundary: the next lane's word carries them unless I end the run
+    if (last_in_run && a + (uint32_t)ncol > 8u) store_partial(q + 8, x >> (64u - sh), 0u, a + (uint32_t)ncol - 8u);
 }
 
 template <bool FAST>
@@ -282,7 +323,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecPa
                 *reinterpret_cast<int4 *>(&S.ctl[s].part) = make_int4((int)p, 0, pi.f, pi.nt);
                 *reinterpret_cast<uint4 *>(&S.ctl[s].pres) =
                     make_uint4(res, kres, mres, (uint32_t)(8 * pi.y0) * (uint32_t)g.W + 8u * (uint32_t)pi.tx0);
-                *reinterpret_cast<int2 *>(&S.ctl[s].y0) = make_int2(pi.y0, pi.tx0);
+                *reinterpret_cast<int4 *>(&S.ctl[s].y0) = make_int4(pi.y0, pi.tx0, pi.ntx, 0);
             }
             const uint32_t total = __reduce_add_sync(0xffffffffu, lane < 3 ? len : 0u);
             __syncwarp();
@@ -351,20 +392,17 @@ __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecPa
                         rp += rowstride;
                     }
                 }
-            } else if (valid) {
+            } else {
                 // crop the padding (dbde_util.cpp:281-289): only rows < H and columns < W are written
-                const int rows_valid = min(8, g.H - 8 * (S.ctl[s].y0 + sb));
-                const int ncol = min(8, g.W - 8 * (S.ctl[s].tx0 + stx));
+                const int4 c2 = *reinterpret_cast<const int4 *>(&S.ctl[s].y0);      // y0, tx0, ntx
+                const int rows_valid = valid ? min(8, g.H - 8 * (c2.x + sb)) : 0;
+                const int ncol = min(8, g.W - 8 * (c2.y + stx));
+                const bool first_in_run = lane == 0 || stx == 0;
+                const bool last_in_run = lane == 31 || stx == c2.z - 1 || tid + 1 >= c0.w;
 #pragma unroll
                 for (int r = 0; r < 8; r++) {
-                    if (r < rows_valid) {
-                        if (ncol == 8 && (((uintptr_t)rp) & 7) == 0) {
-                            *reinterpret_cast<uint2 *>(rp) = make_uint2(px[2 * r], px[2 * r + 1]);
-                        } else {
-                            const uint64_t x = ((uint64_t)px[2 * r + 1] << 32) | px[2 * r];
-                            for (int c = 0; c < ncol; c++) rp[c] = (uint8_t)(x >> (8 * c));
-                        }
-                    }
+                    store_row_generic(rp, ((uint64_t)px[2 * r + 1] << 32) | px[2 * r], ncol, r < rows_valid, first_in_run,
+                                      last_in_run);
                     rp += rowstride;
                 }
             }
