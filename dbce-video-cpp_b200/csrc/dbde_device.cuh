@@ -195,11 +195,21 @@ __device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t *desc, uns
 }
 
 // ------------------------------------------------------------------ warp scan
+// shfl.up hands back "was my source lane in range" as a predicate, so a scan step is SHFL + one
+// predicated add (no lane compares).
 __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, int lane) {
+    (void)lane;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
-        if (lane >= d) v += t;
+        asm volatile(
+            "{\n"
+            ".reg .u32 t;\n"
+            ".reg .pred p;\n"
+            "shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n"
+            "@p add.u32 %0, %0, t;\n"
+            "}"
+            : "+r"(v)
+            : "r"(d));
     }
     return v;
 }

@@ -158,6 +158,18 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
             const uint8_t *fptr = P.frames + (size_t)pi.f * fbytes;
             uint8_t *stage = stages + (size_t)s * g.stage_bytes;
             const int nrows = pi.nbands * 8;
+            if (FAST && g.pitch == g.W) {
+                // full-width partitions of tightly packed rows: the bands are ONE contiguous run in
+                // memory and in the stage -> a single bulk copy (2048-pixel-wide frames: 16 KiB)
+                if (lane == 0) {
+                    const uint32_t bytes = (uint32_t)nrows * (uint32_t)g.W;
+                    *reinterpret_cast<int4 *>(&S.ctl[s].part) = make_int4((int)p, pi.f, pi.tfirst, pi.nt);
+                    *reinterpret_cast<int4 *>(&S.ctl[s].q) = make_int4(pi.q, pi.y0, pi.tx0, 0);
+                    mbar_arrive_expect_tx(&S.full[s], bytes);
+                    tma_load_1d(stage, fptr + (size_t)(8 * pi.y0) * g.W, bytes, &S.full[s]);
+                }
+                continue;
+            }
             const int rowbytes = min(8 * pi.ntx, g.W - 8 * pi.tx0);
             // each lane owns rows lane, lane+32
             uint32_t mybytes = 0;
