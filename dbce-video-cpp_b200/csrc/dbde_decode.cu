@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecPa
             const uint32_t status = nx_status, v = nx_v;
             const uint64_t off = nx_off;
             prefetch(p + gridDim.x);
-            mbar_wait(&S.empty[s], ph ^ 1);
+            mbar_wait_sleepy(&S.empty[s], ph ^ 1);
             if (p >= P.nparts) {
                 if (lane == 0) {
                     S.ctl[s].part = -1;

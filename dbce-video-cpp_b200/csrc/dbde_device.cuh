@@ -79,22 +79,37 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// The suspend-time hint lets the hardware park the warp until the phase flips (or the hint expires)
-// instead of re-issuing YIELD/TRYWAIT/BRA: waiting warps then cost almost no issue slots.
-#ifndef DBDE_MBAR_SUSPEND_NS
-#define DBDE_MBAR_SUSPEND_NS 20000
-#endif
-constexpr uint32_t kMbarSuspendNs = DBDE_MBAR_SUSPEND_NS;
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
-        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendNs) : "memory");
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// For the service warps (producer, scan), which spend most of their life waiting: a failed try_wait
+// comes back after well under 100 ns (ncu: ~45 polls per partition per service warp, 10 % of all issued
+// instructions), so they sleep between polls and leave the issue slots to the tile warps.  The
+// added wake-up latency is hidden by the stages the producer runs ahead / the deferred copy-out.
+#ifndef DBDE_SERVICE_SLEEP_NS
+#define DBDE_SERVICE_SLEEP_NS 256
+#endif
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE_S;\n"
+        "LAB_WAIT_S:\n"
+        "nanosleep.u32 %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE_S;\n"
+        "bra LAB_WAIT_S;\n"
+        "DONE_S:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)DBDE_SERVICE_SLEEP_NS) : "memory");
 }
 // bulk TMA, global -> shared, completion on an mbarrier (SASS: UBLKCP).  16-byte aligned both sides.
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {

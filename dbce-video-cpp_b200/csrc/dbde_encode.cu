@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
         for (unsigned it = 0;; it++) {
             const int s = it % kEncStages;
             const uint32_t ph = (it / kEncStages) & 1;
-            mbar_wait(&S.empty[s], ph ^ 1);
+            mbar_wait_sleepy(&S.empty[s], ph ^ 1);
             unsigned t = 0;
             if (lane == 0) t = atomicAdd(P.ticket, 1u);
             t = __shfl_sync(0xffffffffu, t, 0);
@@ -210,12 +210,12 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
         for (unsigned it = 0;; it++) {
             const int s = it % kEncStages;
             const uint32_t ph = (it / kEncStages) & 1;
-            mbar_wait(&S.full[s], ph);
+            mbar_wait_sleepy(&S.full[s], ph);
             const int4 c0 = *reinterpret_cast<const int4 *>(&S.ctl[s].part);
             if (c0.x < 0) break;
             const unsigned p = (unsigned)c0.x;
             const int f = c0.y, q = S.ctl[s].q;
-            mbar_wait(&S.aggbar[s], ph);
+            mbar_wait_sleepy(&S.aggbar[s], ph);
             const uint32_t wt = lane < kConsumerWarps ? S.warptot[s][lane] : 0u;
             const uint64_t agg = __reduce_add_sync(0xffffffffu, wt);
             uint64_t excl = 0;                      // U64 words of this frame before this partition
