@@ -4,6 +4,7 @@
 #include "../../include/dbde_b200.h"
 #include "dbde_kernels.h"
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -354,6 +355,79 @@ static int ensure_slot(dbde_b200_ctx *c, HostSlot &s, size_t need_a, size_t need
     return 0;
 }
 
+// Where the next chunk's records go in the output stream.  Chunks are claimed strictly in chunk
+// order -- by one worker (plain encode_host) or by several (encode_host_sharded: chunk ci belongs to
+// worker ci mod G) -- so the records land back to back without any pass over the bytes afterwards.
+struct EncSequencer {
+    std::atomic<int> next{0};      // the chunk whose position is claimed next
+    std::atomic<int> err{0};       // first failure; waiting workers bail out on it
+    size_t out_pos = 0;            // guarded by `next`
+};
+
+// Worker `my` of `nworkers`: encodes chunks my, my + nworkers, ... of the batch on context c.
+static int encode_host_worker(dbde_b200_ctx *c, const uint8_t *frames_host, int W, int H, uint64_t first_index,
+                              int nframes, uint8_t *out_host, size_t out_capacity, uint64_t *frame_offsets_host,
+                              int chunk, int my, int nworkers, EncSequencer *seq) {
+    CK(cudaSetDevice(c->device));
+    const size_t px = (size_t)W * H;
+    const size_t delta = payload_align_delta(W, H);
+    const size_t need_a = px * chunk + 32, need_b = dbde_b200_stream_bound(W, H, chunk) + 32;
+    const int nchunks = (nframes + chunk - 1) / chunk;
+    const int mine = nchunks > my ? (nchunks - my + nworkers - 1) / nworkers : 0;
+    const int ns = mine < c->nslots ? mine : c->nslots;            // a one-frame call sets up one slot
+    for (int i = 0; i < ns; i++) {
+        int rc = ensure_slot(c, c->slots[i], need_a, need_b, need_b, chunk);
+        if (rc) return rc;
+    }
+    const size_t stride = dbde_b200_slot_stride(W, H);
+    // finish(): wait for a chunk's kernels, learn the record sizes, claim the chunk's place in the
+    // stream, and queue ONE D2H copy of its records -- already laid back to back on the device.
+    auto finish = [&](int li) -> int {
+        HostSlot &s = c->slots[li % ns];
+        const int ci = my + li * nworkers;
+        CK(cudaEventSynchronize(s.ev));
+        uint64_t total = 0;
+        for (int i = 0; i < s.n; i++) total += s.h_size[i];
+        while (seq->next.load(std::memory_order_acquire) != ci) {
+            if (seq->err.load(std::memory_order_relaxed)) return DBDE_B200_E_INVALID;   // another worker failed
+            std::this_thread::yield();
+        }
+        const size_t pos = seq->out_pos;
+        if (pos + total > out_capacity) return fail(DBDE_B200_E_CAPACITY, "encode_host: out_capacity too small");
+        seq->out_pos = pos + total;
+        seq->next.store(ci + 1, std::memory_order_release);
+        uint64_t run = pos;
+        for (int i = 0; i < s.n; i++) {
+            frame_offsets_host[s.first + i] = run;
+            run += s.h_size[i];
+        }
+        CK(cudaMemcpyAsync(out_host + pos, s.d_c, total, cudaMemcpyDeviceToHost, s.st));
+        return 0;
+    };
+    int pending = -1, rc_all = 0;
+    for (int li = 0; li < mine && !rc_all; li++) {
+        HostSlot &s = c->slots[li % ns];
+        const int ci = my + li * nworkers;
+        CK(cudaStreamSynchronize(s.st));            // the slot's previous chunk has fully drained
+        s.first = ci * chunk;
+        s.n = nframes - s.first < chunk ? nframes - s.first : chunk;
+        CK(cudaMemcpyAsync(s.d_a, frames_host + px * s.first, px * s.n, cudaMemcpyHostToDevice, s.st));
+        rc_all = dbde_b200_encode_device(c, s.d_a, W, H, first_index + s.first, s.n, s.d_b + delta, need_b - 32, stride,
+                                         s.d_off, s.d_size, s.st);
+        if (rc_all) break;
+        CK(cudaMemcpyAsync(s.h_size, s.d_size, 8 * (size_t)s.n, cudaMemcpyDeviceToHost, s.st));
+        CK(launch_compact(s.d_b + delta, stride, s.d_size, s.n, s.d_c, s.st));
+        c->launches += 1;
+        CK(cudaEventRecord(s.ev, s.st));
+        if (pending >= 0) rc_all = finish(pending);
+        pending = li;
+    }
+    if (!rc_all && pending >= 0) rc_all = finish(pending);
+    for (auto &s : c->slots)
+        if (s.st) cudaStreamSynchronize(s.st);
+    return rc_all;
+}
+
 extern "C" int dbde_b200_encode_host(dbde_b200_ctx *c, const uint8_t *frames_host, int W, int H,
                                      uint64_t first_index, int nframes, uint8_t *out_host, size_t out_capacity,
                                      uint64_t *frame_offsets_host) {
@@ -363,58 +437,11 @@ extern "C" int dbde_b200_encode_host(dbde_b200_ctx *c, const uint8_t *frames_hos
         if (frame_offsets_host) frame_offsets_host[0] = 0;
         return 0;
     }
-    CK(cudaSetDevice(c->device));
-    const size_t px = (size_t)W * H;
-    const int chunk = default_chunk(c, W, H, nframes);
-    const size_t delta = payload_align_delta(W, H);
-    const size_t need_a = px * chunk + 32, need_b = dbde_b200_stream_bound(W, H, chunk) + 32;
-    const int nchunks = (nframes + chunk - 1) / chunk;
-    const int ns = nchunks < c->nslots ? nchunks : c->nslots;      // a one-frame call sets up one slot
-    for (int i = 0; i < ns; i++) {
-        int rc = ensure_slot(c, c->slots[i], need_a, need_b, need_b, chunk);
-        if (rc) return rc;
-    }
-    const size_t stride = dbde_b200_slot_stride(W, H);
-    size_t out_pos = 0;
-    int rc_all = 0;
-    // finish(): wait for a chunk's kernels, learn the record sizes, and queue ONE D2H copy of the
-    // chunk's records -- already laid back to back on the device -- to the running offset in
-    // out_host (the host-side concatenation across chunks).
-    auto finish = [&](int ci) -> int {
-        HostSlot &s = c->slots[ci % ns];
-        CK(cudaEventSynchronize(s.ev));
-        uint64_t total = 0;
-        for (int i = 0; i < s.n; i++) {
-            frame_offsets_host[s.first + i] = out_pos + total;
-            total += s.h_size[i];
-        }
-        if (out_pos + total > out_capacity) return fail(DBDE_B200_E_CAPACITY, "encode_host: out_capacity too small");
-        CK(cudaMemcpyAsync(out_host + out_pos, s.d_c, total, cudaMemcpyDeviceToHost, s.st));
-        out_pos += total;
-        return 0;
-    };
-    int pending = -1;
-    for (int ci = 0; ci < nchunks && !rc_all; ci++) {
-        HostSlot &s = c->slots[ci % ns];
-        CK(cudaStreamSynchronize(s.st));            // the slot's previous chunk has fully drained
-        s.first = ci * chunk;
-        s.n = nframes - s.first < chunk ? nframes - s.first : chunk;
-        CK(cudaMemcpyAsync(s.d_a, frames_host + px * s.first, px * s.n, cudaMemcpyHostToDevice, s.st));
-        rc_all = dbde_b200_encode_device(c, s.d_a, W, H, first_index + s.first, s.n, s.d_b + delta,
-                                         need_b - 32, stride, s.d_off, s.d_size, s.st);
-        if (rc_all) break;
-        CK(cudaMemcpyAsync(s.h_size, s.d_size, 8 * (size_t)s.n, cudaMemcpyDeviceToHost, s.st));
-        CK(launch_compact(s.d_b + delta, stride, s.d_size, s.n, s.d_c, s.st));
-        c->launches += 1;
-        CK(cudaEventRecord(s.ev, s.st));
-        if (pending >= 0) rc_all = finish(pending);
-        pending = ci;
-    }
-    if (!rc_all && pending >= 0) rc_all = finish(pending);
-    for (auto &s : c->slots)
-        if (s.st) cudaStreamSynchronize(s.st);
-    if (rc_all) return rc_all;
-    frame_offsets_host[nframes] = out_pos;
+    EncSequencer seq;
+    int rc = encode_host_worker(c, frames_host, W, H, first_index, nframes, out_host, out_capacity, frame_offsets_host,
+                                default_chunk(c, W, H, nframes), 0, 1, &seq);
+    if (rc) return rc;
+    frame_offsets_host[nframes] = seq.out_pos;
     return 0;
 }
 
@@ -500,41 +527,39 @@ extern "C" int dbde_b200_decode_host(dbde_b200_ctx *c, const uint8_t *stream_hos
 extern "C" int dbde_b200_encode_host_sharded(dbde_b200_ctx **ctxs, int nctx, const uint8_t *frames_host, int W,
                                              int H, uint64_t first_index, int nframes, uint8_t *out_host,
                                              size_t out_capacity, uint64_t *frame_offsets_host) {
-    if (!ctxs || nctx < 1 || !dims_ok(W, H, nframes)) return fail(DBDE_B200_E_INVALID, "encode_host_sharded: bad argument");
-    if (nctx == 1 || nframes < nctx)
-        return dbde_b200_encode_host(ctxs[0], frames_host, W, H, first_index, nframes, out_host, out_capacity,
-                                     frame_offsets_host);
-    const size_t stride = dbde_b200_slot_stride(W, H), px = (size_t)W * H;
-    if (out_capacity < stride * (size_t)nframes)
-        return fail(DBDE_B200_E_CAPACITY, "encode_host_sharded: out_capacity < dbde_b200_stream_bound()");
-    std::vector<int> rc(nctx, 0), a(nctx + 1);
+    if (!ctxs || nctx < 1 || !dims_ok(W, H, nframes) || (nframes > 0 && (!frames_host || !out_host || !frame_offsets_host)))
+        return fail(DBDE_B200_E_INVALID, "encode_host_sharded: bad argument");
+    for (int g = 0; g < nctx; g++)
+        if (!ctxs[g]) return fail(DBDE_B200_E_INVALID, "encode_host_sharded: null context");
+    if (nframes == 0) {
+        frame_offsets_host[0] = 0;
+        return 0;
+    }
+    // The batch is cut into contiguous frame ranges of one chunk each; range ci goes to context
+    // ci mod G.  Every context streams its ranges over its own PCIe link, and the ranges' records are
+    // placed in stream order as their sizes become known (EncSequencer): the stream is complete when
+    // the last copy lands -- no shard is moved afterwards.
+    const int chunk = default_chunk(ctxs[0], W, H, nframes);
+    EncSequencer seq;
+    std::vector<int> rc(nctx, 0);
     std::vector<std::string> err(nctx);
-    for (int g = 0; g <= nctx; g++) a[g] = (int)((long long)nframes * g / nctx);
-    std::vector<std::vector<uint64_t>> offs(nctx);
     std::vector<std::thread> th;
     for (int g = 0; g < nctx; g++) {
-        offs[g].resize(a[g + 1] - a[g] + 1);
         th.emplace_back([&, g]() {
-            // shard g lands at its worst-case base; it is slid down once the earlier shards' sizes are known
-            rc[g] = dbde_b200_encode_host(ctxs[g], frames_host + px * a[g], W, H, first_index + a[g], a[g + 1] - a[g],
-                                          out_host + stride * (size_t)a[g], stride * (size_t)(a[g + 1] - a[g]),
-                                          offs[g].data());
-            if (rc[g]) err[g] = dbde_b200_last_error();
+            rc[g] = encode_host_worker(ctxs[g], frames_host, W, H, first_index, nframes, out_host, out_capacity,
+                                       frame_offsets_host, chunk, g, nctx, &seq);
+            if (rc[g]) {
+                err[g] = dbde_b200_last_error();
+                seq.err.store(rc[g], std::memory_order_relaxed);
+            }
         });
     }
     for (auto &t : th) t.join();
     for (int g = 0; g < nctx; g++)
-        if (rc[g]) return fail(rc[g], err[g].c_str());
-    size_t pos = 0;
-    for (int g = 0; g < nctx; g++) {
-        const int n = a[g + 1] - a[g];
-        const size_t bytes = offs[g][n];
-        const uint8_t *src = out_host + stride * (size_t)a[g];
-        if (out_host + pos != src) memmove(out_host + pos, src, bytes);
-        for (int i = 0; i < n; i++) frame_offsets_host[a[g] + i] = pos + offs[g][i];
-        pos += bytes;
-    }
-    frame_offsets_host[nframes] = pos;
+        if (rc[g] && !err[g].empty()) return fail(rc[g], err[g].c_str());
+    for (int g = 0; g < nctx; g++)
+        if (rc[g]) return fail(rc[g], "encode_host_sharded: a worker failed");
+    frame_offsets_host[nframes] = seq.out_pos;
     return 0;
 }
 

@@ -62,7 +62,10 @@ __global__ void __launch_bounds__(256) dbde_decode_scan_kernel(const DecParams P
     // reduced so four global loads are in flight per lane.
     const uint8_t *dp = rec + 24;
     bool big = false;
-    constexpr int kBatch = 4;
+#ifndef DBDE_SCAN_BATCH
+#define DBDE_SCAN_BATCH 4
+#endif
+    constexpr int kBatch = DBDE_SCAN_BATCH;
     for (int q0 = warp * kBatch; q0 < g.ppf; q0 += 8 * kBatch) {
         uint32_t lo[kBatch], hi[kBatch];
 #pragma unroll

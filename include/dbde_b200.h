@@ -113,12 +113,14 @@ DBDE_B200_API int dbde_b200_decode_host(dbde_b200_ctx *ctx, const uint8_t *strea
                                         uint8_t *frames_host, uint32_t *status_host, uint64_t *indices_host);
 
 /* ---- multi-GPU: contiguous frame ranges, one host thread per context, host-side concatenation -- */
-/* Frames carry no inter-frame state (dbde_util.cpp:146), so a long video shards by frame range:
- * context g encodes frames [g*n/G, (g+1)*n/G) on its own GPU over its own PCIe link and the
- * shards' records are laid back to back in out_host (an exclusive prefix sum over the shard byte
- * counts; no device-to-device traffic, no collective).  Output is byte-identical to
- * dbde_b200_encode_host on one GPU.  Each ctxs[g] must be a distinct context (they may share a
- * device); out_capacity must be >= dbde_b200_stream_bound(W, H, nframes). */
+/* Frames carry no inter-frame state (dbde_util.cpp:146), so a long video shards by frame range with
+ * no device-to-device traffic and no collective.  encode: the batch is cut into contiguous ranges of
+ * one staging chunk each, range i goes to context i mod G, every context streams its ranges over
+ * its own PCIe link, and the ranges' records are placed in stream order as their sizes become
+ * known (an exclusive prefix sum over range byte counts, taken on the host as the ranges finish).
+ * decode: context g takes frames [g*n/G, (g+1)*n/G).  Output is byte-identical to the one-GPU calls.
+ * Each ctxs[g] must be a distinct context (they may share a device); out_capacity must be
+ * >= dbde_b200_stream_bound(W, H, nframes). */
 DBDE_B200_API int dbde_b200_encode_host_sharded(dbde_b200_ctx **ctxs, int nctx, const uint8_t *frames_host, int W,
                                                 int H, uint64_t first_index, int nframes, uint8_t *out_host,
                                                 size_t out_capacity, uint64_t *frame_offsets_host);
