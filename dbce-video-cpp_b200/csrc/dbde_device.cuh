@@ -1,8 +1,9 @@
 // DBDE B200 codec -- device-side building blocks (sm_100a only).
 //
 // Everything here is written for Blackwell: bulk-TMA (cp.async.bulk -> SASS UBLKCP) staged
-// through mbarrier pipelines, VIMNMX3.U16x2 byte-min reduction, REDUX warp sums, and a
-// single-word decoupled look-back.  No tensor cores: the path has no contraction.
+// through mbarrier pipelines, VIMNMX3.U16x2 byte-min reduction, REDUX warp sums, a predicate-
+// returning SHFL scan, and a single-word decoupled look-back.  No tensor cores: the path has no
+// contraction.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -118,18 +119,6 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, ui
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-// bulk TMA, shared -> global, bulk-group completion.
-__device__ __forceinline__ void tma_store_1d(void *gdst, const void *smem_src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() {
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // order this thread's generic-proxy smem accesses against later async-proxy (TMA) accesses
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -146,9 +135,6 @@ __device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) {
 // streaming global stores (written once, never re-read by this kernel)
 __device__ __forceinline__ void st_stream_u64(void *p, uint64_t v) {
     asm volatile("st.global.cs.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ void st_stream_v2u64(void *p, uint64_t a, uint64_t b) {
-    asm volatile("st.global.cs.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 __device__ __forceinline__ void st_stream_v4u32(void *p, uint4 v) {
     asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -306,11 +292,6 @@ __device__ __forceinline__ void split_fields(const uint32_t (&x)[16], uint32_t (
         q[i] = v & fmask;
     }
 }
-
-// staging swizzle at U64 granularity: spreads equal-depth lanes (stride K words) over the banks
-__device__ __forceinline__ uint32_t swz(uint32_t a) { return a ^ ((a >> 4) & 15u); }
-// the same permutation on BYTE offsets of U64 words (8*a -> 8*swz(a)): one shift + one fused and-xor
-__device__ __forceinline__ uint32_t swz_bytes(uint32_t byte_off) { return byte_off ^ ((byte_off >> 4) & 0x78u); }
 
 // unaligned-safe shared loads for the generic (odd width / odd offset) paths
 __device__ __forceinline__ uint32_t lds_u32_unaligned(const uint8_t *p) {

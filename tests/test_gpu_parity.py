@@ -332,3 +332,58 @@ def test_the_references_own_test_program_passes_against_this_library():
     assert len(la) == len(lb) and len(la) > 10
     assert la[:-3] == lb[:-3]
     assert "!! 0 of 5193728" in a.stdout and "Failed iteration" not in a.stdout
+
+
+def test_sharded_encode_interleaves_chunk_ranges_in_stream_order(codec):
+    """encode_host_sharded deals chunk-sized frame ranges round-robin to the contexts and places them
+    in stream order as their sizes become known: many small chunks over three contexts (on a multi-GPU
+    box: spread over the devices), uneven last chunk, and fewer chunks than contexts."""
+    ndev = pkg.load().dbde_b200_device_count()
+    group = [codec] + [pkg.Codec(i % ndev) for i in range(1, 3)]
+    try:
+        for n, chunk in [(29, 2), (29, 3), (2, 5), (1, 1), (16, 1)]:
+            fr = synth.gen_frames("mix", n, 200, 104, f0=n)
+            want, sizes = ORA.pack_frames(fr, 1000)
+            group[0].set_chunk_frames(chunk)           # the sharded call takes its chunk size from context 0
+            try:
+                stream, offs = pkg.encode_host_sharded(group, fr, 1000)
+            finally:
+                group[0].set_chunk_frames(0)
+            assert len(stream) == len(want) and (stream == want).all(), (n, chunk)
+            assert offs.tolist() == [0] + np.cumsum(sizes).tolist()
+            dec, status, index = pkg.decode_host_sharded(group, stream, offs[:-1], 200, 104)
+            assert (status == 0).all() and index.tolist() == list(range(1000, 1000 + n)) and (dec == fr).all()
+    finally:
+        for c in group[1:]:
+            c.close()
+
+
+def test_sharded_encode_reports_a_short_output_buffer_instead_of_hanging(codec):
+    """a worker that cannot place its range must fail the whole call (and release the workers waiting
+    for their turn), not deadlock or write past the buffer"""
+    import ctypes as C
+    lib = codec.lib
+    fr = synth.gen_frames("noise", 12, 64, 64)
+    others = [pkg.Codec(0)]
+    try:
+        codec.set_chunk_frames(2)
+        cap = 3 * (32 + 66 * 64) + 100                 # room for about three of the twelve records
+        out = np.full(cap + 4096, 0xEE, dtype=np.uint8)
+        offs = np.zeros(13, dtype=np.uint64)
+        arr = (C.c_void_p * 2)(codec.h.value, others[0].h.value)
+        rc = lib.dbde_b200_encode_host_sharded(arr, 2, fr.ctypes.data, 64, 64, 0, 12, out.ctypes.data, cap, offs.ctypes.data)
+        assert rc != 0
+        assert (out[cap:] == 0xEE).all()               # nothing beyond the stated capacity was touched
+        rc = lib.dbde_b200_encode_host(codec.h, fr.ctypes.data, 64, 64, 0, 12, out.ctypes.data, cap, offs.ctypes.data)
+        assert rc == pkg.load().dbde_b200_encode_host(codec.h, fr.ctypes.data, 64, 64, 0, 12, out.ctypes.data, cap,
+                                                      offs.ctypes.data) != 0
+        assert (out[cap:] == 0xEE).all()
+        # and the contexts still work afterwards
+        codec.set_chunk_frames(0)
+        want, _ = ORA.pack_frames(fr, 0)
+        stream, _ = pkg.encode_host_sharded([codec] + others, fr, 0)
+        assert (stream == want).all()
+    finally:
+        codec.set_chunk_frames(0)
+        for c in others:
+            c.close()
