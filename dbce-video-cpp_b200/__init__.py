@@ -32,6 +32,8 @@ C_SYMBOLS = [
     "dbde_b200_encode_device", "dbde_b200_decode_device", "dbde_b200_encode_host", "dbde_b200_decode_host",
     "dbde_b200_encode_host_sharded", "dbde_b200_decode_host_sharded",
     "dbde_b200_index_stream", "dbde_b200_set_chunk_frames", "dbde_b200_kernel_launches",
+    "dbde_b200_writer_open", "dbde_b200_writer_append", "dbde_b200_writer_close",
+    "dbde_b200_reader_open", "dbde_b200_reader_next", "dbde_b200_reader_close", "dbde_b200_file_last_error",
 ]
 # the reference's C++ entry points (include/dbde_util.h), by mangled name
 CXX_SYMBOLS = {
@@ -99,6 +101,15 @@ def load():
     lib.dbde_b200_set_chunk_frames.argtypes = [C.c_void_p, C.c_int]
     lib.dbde_b200_kernel_launches.restype = C.c_uint64
     lib.dbde_b200_kernel_launches.argtypes = [C.c_void_p]
+    lib.dbde_b200_writer_open.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_uint64, C.POINTER(C.c_void_p)]
+    lib.dbde_b200_writer_append.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.dbde_b200_writer_close.argtypes = [C.c_void_p, _u64p, _u64p]
+    lib.dbde_b200_reader_open.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                          C.POINTER(C.c_double), C.POINTER(C.c_void_p)]
+    lib.dbde_b200_reader_next.restype = C.c_long
+    lib.dbde_b200_reader_next.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.dbde_b200_reader_close.argtypes = [C.c_void_p]
+    lib.dbde_b200_file_last_error.restype = C.c_char_p
     return lib
 
 
@@ -265,6 +276,52 @@ def decode_host_sharded(codecs, stream, offsets, W, H):
     if rc:
         raise DbdeError("decode_host_sharded failed (%d): %s" % (rc, lib.dbde_b200_last_error().decode()))
     return frames, status, index
+
+
+def write_file(codec, path, frames, hz=30.0, first_index=0, batch=16):
+    """dbde_b200_writer_*: stream `frames` (N,H,W) into a .dbde file in batches -> (frames, bytes) written"""
+    lib = codec.lib
+    frames = np.ascontiguousarray(frames, dtype=np.uint8)
+    N, H, W = frames.shape
+    w = C.c_void_p()
+    if lib.dbde_b200_writer_open(codec.h, path.encode(), W, H, hz, first_index, C.byref(w)):
+        raise DbdeError("writer_open: " + lib.dbde_b200_file_last_error().decode())
+    try:
+        for a in range(0, N, batch):
+            part = frames[a:a + batch]
+            if lib.dbde_b200_writer_append(w, part.ctypes.data, len(part)):
+                raise DbdeError("writer_append: " + lib.dbde_b200_file_last_error().decode())
+    finally:
+        nf, nb = C.c_uint64(), C.c_uint64()
+        rc = lib.dbde_b200_writer_close(w, C.byref(nf), C.byref(nb))
+    if rc:
+        raise DbdeError("writer_close: " + lib.dbde_b200_file_last_error().decode())
+    return nf.value, nb.value
+
+
+def read_file(codec, path, batch=16, fill=0xCD):
+    """dbde_b200_reader_*: -> ((W, H, hz), frames (N,H,W), indices[N], status[N])"""
+    lib = codec.lib
+    r, W, H, hz = C.c_void_p(), C.c_int(), C.c_int(), C.c_double()
+    if lib.dbde_b200_reader_open(codec.h, path.encode(), batch, C.byref(W), C.byref(H), C.byref(hz), C.byref(r)):
+        raise DbdeError("reader_open: " + lib.dbde_b200_file_last_error().decode())
+    out, idx, st = [], [], []
+    try:
+        while True:
+            fr = np.full((batch, H.value, W.value), fill, dtype=np.uint8)
+            ii = np.zeros(batch, dtype=np.uint64)
+            ss = np.zeros(batch, dtype=np.uint32)
+            n = lib.dbde_b200_reader_next(r, fr.ctypes.data, batch, ii.ctypes.data, ss.ctypes.data)
+            if n < 0:
+                raise DbdeError("reader_next: " + lib.dbde_b200_file_last_error().decode())
+            if n == 0:
+                break
+            out.append(fr[:n]); idx.append(ii[:n]); st.append(ss[:n])
+    finally:
+        lib.dbde_b200_reader_close(r)
+    if not out:
+        return (W.value, H.value, hz.value), np.zeros((0, H.value, W.value), np.uint8), np.zeros(0, np.uint64), np.zeros(0, np.uint32)
+    return (W.value, H.value, hz.value), np.concatenate(out), np.concatenate(idx), np.concatenate(st)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -134,6 +134,34 @@ DBDE_B200_API int dbde_b200_decode_host_sharded(dbde_b200_ctx **ctxs, int nctx, 
 DBDE_B200_API long dbde_b200_index_stream(const uint8_t *stream_host, size_t stream_bytes, int W, int H,
                                           uint64_t *frame_offsets, long max_frames);
 
+/* ---- .dbde files: 28-byte video header + frame records back to back ------------- */
+/* The container the reference's walker reads (dbde_util.cpp:362-426; dbde_start_file_walk /
+ * dbde_walk_a_file / dbde_end_file_walk in include/dbde_util.h remain available as the drop-in).
+ * The reference has no writer (only dbde_util_test.cpp:204-211); these stream whole batches through
+ * the GPU codec with disk I/O overlapped on a helper thread.  A writer/reader belongs to the thread
+ * that owns its context. */
+typedef struct dbde_b200_writer dbde_b200_writer;
+typedef struct dbde_b200_reader dbde_b200_reader;
+/* creates/truncates `path` and writes the video header {3, H, W, frame_hz} (dbde_util.cpp:198-209);
+ * frame indices start at first_index */
+DBDE_B200_API int dbde_b200_writer_open(dbde_b200_ctx *ctx, const char *path, int W, int H, double frame_hz,
+                                        uint64_t first_index, dbde_b200_writer **out);
+/* encodes nframes frames (host memory, tightly packed) and appends their records; the bytes reach
+ * the file while the next batch is being encoded */
+DBDE_B200_API int dbde_b200_writer_append(dbde_b200_writer *w, const uint8_t *frames_host, int nframes);
+DBDE_B200_API int dbde_b200_writer_close(dbde_b200_writer *w, uint64_t *frames_written, uint64_t *bytes_written);
+/* opens `path`, parses the video header (rejects u64s != 3 and the reference's size limits,
+ * dbde_util.cpp:374-378); batch_frames = frames decoded per GPU batch (<= 0: 16) */
+DBDE_B200_API int dbde_b200_reader_open(dbde_b200_ctx *ctx, const char *path, int batch_frames, int *W, int *H,
+                                        double *frame_hz, dbde_b200_reader **out);
+/* decodes the next <= min(max_frames, batch_frames) frames into frames_host; returns how many were
+ * handed out, 0 at the end of the file, < 0 on error.  status[i] != 0 marks a rejected record (pixels
+ * untouched); reading stops after the first one, like the reference's walker (dbde_util.cpp:416). */
+DBDE_B200_API long dbde_b200_reader_next(dbde_b200_reader *r, uint8_t *frames_host, int max_frames,
+                                         uint64_t *indices, uint32_t *status);
+DBDE_B200_API int dbde_b200_reader_close(dbde_b200_reader *r);
+DBDE_B200_API const char *dbde_b200_file_last_error(void);
+
 /* Tuning knob for the host path: frames per staged chunk (default: ~64 MiB of pixels). */
 DBDE_B200_API int dbde_b200_set_chunk_frames(dbde_b200_ctx *ctx, int frames);
 

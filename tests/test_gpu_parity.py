@@ -387,3 +387,43 @@ def test_sharded_encode_reports_a_short_output_buffer_instead_of_hanging(codec):
         codec.set_chunk_frames(0)
         for c in others:
             c.close()
+
+
+def test_file_writer_and_reader_roundtrip_against_the_oracle_file(codec, dropin):
+    """dbde_b200_writer_* must produce byte for byte the file the reference's functions
+    would (dbde_pack_video_header + dbde_pack_frame per frame, dbde_util_test.cpp:204-211), for batch
+    sizes that do and do not divide the frame count; dbde_b200_reader_* and the reference-compatible
+    walker must both read it back; a corrupted record stops the reader like the walker (:416)."""
+    for W, H, N, batch in [(10, 10, 9, 4), (136, 72, 23, 5), (264, 136, 12, 16), (1001, 1003, 3, 2)]:
+        fr = synth.gen_frames("mix", N, W, H, f0=3)
+        stream, sizes = ORA.pack_frames(fr, 500)
+        want = np.concatenate([ORA.pack_video_header(3, H, W, 12.5), stream])
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, "a.dbde")
+            nf, nb = pkg.write_file(codec, path, fr, hz=12.5, first_index=500, batch=batch)
+            got = np.fromfile(path, dtype=np.uint8)
+            assert nf == N and nb == len(want) and len(got) == len(want) and (got == want).all(), (W, H, N, batch)
+            for rb in (1, batch, N + 3):
+                (w, h, hz), frames, idx, st = pkg.read_file(codec, path, batch=rb)
+                assert (w, h, hz) == (W, H, 12.5) and (st == 0).all()
+                assert idx.tolist() == list(range(500, 500 + N)) and (frames == fr).all()
+            vh, frames = dropin.walk_file(path, 4)
+            assert vh == (3, H, W, 12.5) and len(frames) == N and all((img == fr[i]).all() for i, (_, img) in enumerate(frames))
+            # break the depth plane of frame 5 (if there is one): frames 0..4 come back, frame 5 is flagged, then EOF
+            if N > 5:
+                bad = got.copy()
+                off5 = 28 + int(np.sum(sizes[:5]))
+                bad[off5 + 24] = 9                                    # a depth byte > 8
+                bad.tofile(path)
+                _, frames, idx, st = pkg.read_file(codec, path, batch=4, fill=0xCD)
+                assert len(frames) == 6 and (st[:5] == 0).all() and st[5] != 0
+                assert (frames[:5] == fr[:5]).all() and (frames[5] == 0xCD).all()
+            # a file cut in the middle of its last record: the torn record is not handed out
+            got[:len(got) - 7].tofile(path)
+            _, frames, idx, st = pkg.read_file(codec, path, batch=batch)
+            assert len(frames) == N - 1 and (frames == fr[:N - 1]).all()
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "junk.dbde")
+        np.arange(100, dtype=np.uint8).tofile(path)
+        with pytest.raises(pkg.DbdeError):
+            pkg.read_file(codec, path)
