@@ -427,3 +427,42 @@ def test_file_writer_and_reader_roundtrip_against_the_oracle_file(codec, dropin)
         np.arange(100, dtype=np.uint8).tofile(path)
         with pytest.raises(pkg.DbdeError):
             pkg.read_file(codec, path)
+
+
+@pytest.mark.parametrize("kind,N,W,H", [("micro", 256, 2048, 2048), ("mix", 160, 1001, 1003), ("low", 40, 4096, 4096),
+                                        ("noise", 12, 2536, 2048), ("micro", 24, 4096, 4096)])
+def test_baseline_configs_device_resident_at_scale(codec, kind, N, W, H):
+    """BASELINE configs 2-4 (+ the reference's own 2536x2048 noise frame, + micro at 4096^2) as the bench
+    runs them -- generated, encoded and decoded in HBM, hundreds of frames per launch so the persistent
+    kernels, the frame-interleaved tickets and the look-back chains run at depth.  Size-independent
+    properties on the whole batch (decode(encode(x)) == x on the device, every status 0, record sizes
+    consistent with the depth planes) and byte equality with the oracle on sampled records."""
+    px = W * H
+    wh = ((W + 7) // 8) * ((H + 7) // 8)
+    stride = codec.slot_stride(W, H)
+    cap = codec.stream_bound(W, H, N)
+    d_fr, d_dec, d_out = codec.device_alloc(N * px), codec.device_alloc(N * px), codec.device_alloc(cap + 64)
+    d_off, d_sz, d_st, d_ix = codec.device_alloc(8 * N), codec.device_alloc(8 * N), codec.device_alloc(4 * N), codec.device_alloc(8 * N)
+    delta = (16 - (32 + 2 * wh) % 16) % 16
+    try:
+        synth.gen_frames_device(kind, N, W, H, d_fr, seed=42, f0=0)
+        codec.encode_device(d_fr, W, H, 7, N, d_out + delta, cap, d_off, d_sz)
+        codec.decode_device(d_out + delta, cap, d_off, W, H, N, d_dec, d_st, d_ix)
+        sizes = codec.d2h(d_sz, 8 * N, np.uint64)
+        assert (codec.d2h(d_st, 4 * N, np.uint32) == 0).all()
+        assert codec.d2h(d_ix, 8 * N, np.uint64).tolist() == list(range(7, 7 + N))
+        assert codec.d2h(d_off, 8 * N, np.uint64).tolist() == [i * stride for i in range(N)]
+        # whole-batch round trip, compared frame by frame to bound host memory
+        for i in range(N):
+            a, b = codec.d2h(d_fr + i * px, px), codec.d2h(d_dec + i * px, px)
+            assert (a == b).all(), i
+        # sampled records against the oracle, and size == 32 + 2wh + 8 * sum(depth plane)
+        for i in sorted({0, 1, N // 2, N - 1}):
+            rec = codec.d2h(d_out + delta + i * stride, int(sizes[i]))
+            fr = codec.d2h(d_fr + i * px, px).reshape(1, H, W)
+            want, wsz = ORA.pack_frames(fr, 7 + i)
+            assert int(sizes[i]) == int(wsz[0]) and (rec == want).all(), i
+            assert int(sizes[i]) == 32 + 2 * wh + 8 * int(rec[24:24 + wh].astype(np.int64).sum())
+    finally:
+        for p in (d_fr, d_dec, d_out, d_off, d_sz, d_st, d_ix):
+            codec.device_free(p)
