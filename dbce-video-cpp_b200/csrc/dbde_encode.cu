@@ -26,6 +26,8 @@
 
 namespace dbde {
 
+// 4 stages x 16 KiB x 3 CTAs/SM fill the 227 KiB of shared memory; measured on micro-2048: 3 stages
+// -7 %, 5-6 stages at 2 CTAs/SM -19 %, releasing the deferred stage half an iteration earlier -1 %.
 constexpr int kEncStages = 4;
 constexpr int kEncThreads = kTilesPerPart + 64;
 
