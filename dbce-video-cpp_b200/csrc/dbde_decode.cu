@@ -18,9 +18,20 @@
 #include "dbde_device.cuh"
 #include "dbde_kernels.h"
 
+#include <cstdlib>
+
 namespace dbde {
 
 constexpr int kDecStages = 3;
+// The producer keeps at most kDecStages partitions in flight, and fewer when they are large: it
+// does not let the payload bytes of the issued-but-unconsumed partitions exceed this many per CTA.
+// Measured (micro-2048, 4 CTAs/SM): an unconditional depth of 3 runs at 5.32 TB/s, depth 2 at 5.85 --
+// the 25/75 read/write stream is fastest with ~50 KB of reads in flight per SM -- while
+// low-entropy records (1.3 KB per partition) want all three (5.04 vs 4.83 TB/s).
+#ifndef DBDE_DEC_INFLIGHT_BYTES
+#define DBDE_DEC_INFLIGHT_BYTES 6144
+#endif
+constexpr uint32_t kDecInflightBytes = DBDE_DEC_INFLIGHT_BYTES;
 constexpr int kDecThreads = kTilesPerPart + 32;
 constexpr int kDecPayloadBytes = 64 * kTilesPerPart + 32;        // worst-case words + 16-byte hull slack
 constexpr int kDecPlaneBytes = kTilesPerPart + 32;
@@ -282,6 +293,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecPa
             }
         };
         prefetch(p);
+        uint32_t b1 = 0, b2 = 0;                   // payload bytes of the two previous iterations
         for (unsigned it = 0;; it++, p += gridDim.x) {
             const int s = it % kDecStages;
             const uint32_t ph = (it / kDecStages) & 1;
@@ -301,12 +313,20 @@ __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecPa
                     *reinterpret_cast<int2 *>(&S.ctl[s].part) = make_int2((int)p, 1);
                     mbar_arrive(&S.full[s]);
                 }
+                b2 = b1;
+                b1 = 0;
                 continue;
             }
             const PartInfo pi = part_info(g, p);
             const uint8_t *rec = P.stream + off;
             const uint32_t v0 = __shfl_sync(0xffffffffu, v, 0), v8 = __shfl_sync(0xffffffffu, v, kConsumerWarps);
             const uint32_t agg = v8 - v0;
+            // adaptive depth: with large payloads, wait until the partition issued two iterations ago
+            // has been consumed (at most two in flight) before adding this one
+            if (kDecStages > 2 && it >= 2 && 8u * agg + b1 + b2 > kDecInflightBytes)
+                mbar_wait_sleepy(&S.empty[(it - 2) % kDecStages], ((it - 2) / kDecStages) & 1);
+            b2 = b1;
+            b1 = 8u * agg;
             uint8_t *stage = stages + (size_t)s * kDecStageBytes;
             // lane 0: payload words, lane 1: depth bytes, lane 2: minimum bytes (16-byte hulls)
             const uint8_t *src = nullptr;
@@ -425,7 +445,8 @@ cudaError_t launch_decode_scan(const DecParams &P, cudaStream_t stream) {
 }
 
 cudaError_t launch_decode(const DecParams &P, bool fast, int num_sms, cudaStream_t stream) {
-    const size_t smem = dec_smem_bytes(P.g);
+    size_t smem = dec_smem_bytes(P.g);
+    if (const char *e = getenv("DBDE_B200_DEC_PAD_SMEM")) smem += (size_t)atoi(e);   // experiment knob
     auto kern = fast ? dbde_decode_kernel<true> : dbde_decode_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -433,6 +454,10 @@ cudaError_t launch_decode(const DecParams &P, bool fast, int num_sms, cudaStream
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kDecThreads, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
+    if (const char *e = getenv("DBDE_B200_DEC_CTAS")) {      // experiment knob: cap the CTAs per SM
+        const int cap = atoi(e);
+        if (cap >= 1 && cap < occ) occ = cap;
+    }
     unsigned grid = (unsigned)(num_sms * occ);
     if (grid > P.nparts) grid = P.nparts;
     if (grid == 0) return cudaSuccess;
