@@ -466,3 +466,44 @@ def test_baseline_configs_device_resident_at_scale(codec, kind, N, W, H):
     finally:
         for p in (d_fr, d_dec, d_out, d_off, d_sz, d_st, d_ix):
             codec.device_free(p)
+
+
+@pytest.mark.parametrize("W,H,N", [(1001, 1003, 3), (13, 9, 5), (7, 5, 4), (2048, 16, 2), (264, 24, 3), (4100, 12, 2)])
+def test_decoder_and_encoder_never_write_outside_their_buffers(codec, W, H, N):
+    """guard bytes around the decoder's pixel output and the encoder's slots, at every misalignment of
+    the output base: the generic store path assembles aligned 8-byte words across lanes, so a frame's
+    first/last bytes share words with the neighbouring memory and must be written with narrow stores"""
+    px = W * H
+    fr = synth.gen_frames("mix", N, W, H, f0=11)
+    want, sizes = ORA.pack_frames(fr, 0)
+    stride = codec.slot_stride(W, H)
+    G = 64
+    d_fr = codec.device_alloc(N * px + 2 * G + 16)
+    d_out = codec.device_alloc(N * stride + 2 * G + 16)
+    d_dec = codec.device_alloc(N * px + 2 * G + 16)
+    d_off, d_sz, d_st = codec.device_alloc(8 * N), codec.device_alloc(8 * N), codec.device_alloc(4 * N)
+    try:
+        for shift in (0, 1, 3, 4, 7, 8, 13):
+            codec.h2d(d_fr, np.full(N * px + 2 * G + 16, 0x5A, dtype=np.uint8))
+            codec.h2d(d_fr + G + shift, fr)
+            codec.h2d(d_out, np.full(N * stride + 2 * G + 16, 0xEE, dtype=np.uint8))
+            codec.encode_device(d_fr + G + shift, W, H, 0, N, d_out + G + shift, N * stride, d_off, d_sz)
+            out = codec.d2h(d_out, N * stride + 2 * G + 16)
+            assert (out[:G + shift] == 0xEE).all() and (out[G + shift + N * stride:] == 0xEE).all(), shift
+            szs = codec.d2h(d_sz, 8 * N, np.uint64)
+            pos = 0
+            for i in range(N):
+                rec = out[G + shift + i * stride: G + shift + i * stride + int(szs[i])]
+                assert (rec == want[pos:pos + int(szs[i])]).all(), (shift, i)
+                assert (out[G + shift + i * stride + int(szs[i]): G + shift + (i + 1) * stride] == 0xEE).all(), (shift, i)
+                pos += int(szs[i])
+            for dshift in (shift, (shift * 5 + 2) % 16):
+                codec.h2d(d_dec, np.full(N * px + 2 * G + 16, 0xA7, dtype=np.uint8))
+                codec.decode_device(d_out + G + shift, N * stride, d_off, W, H, N, d_dec + G + dshift, d_st, None)
+                dec = codec.d2h(d_dec, N * px + 2 * G + 16)
+                assert (codec.d2h(d_st, 4 * N, np.uint32) == 0).all()
+                assert (dec[G + dshift:G + dshift + N * px].reshape(fr.shape) == fr).all(), (shift, dshift)
+                assert (dec[:G + dshift] == 0xA7).all() and (dec[G + dshift + N * px:] == 0xA7).all(), (shift, dshift)
+    finally:
+        for p in (d_fr, d_out, d_dec, d_off, d_sz, d_st):
+            codec.device_free(p)
