@@ -201,7 +201,7 @@ void dbde_unpack_8x8_partial(uint8_t depth, uint8_t minval, uint8_t *packed, siz
 // batches of `frames_buffered` and handed out one per call.
 namespace {
 struct WalkerSide {
-    std::vector<uint8_t> frames;        // decoded batch
+    uint8_t *frames = nullptr;          // decoded batch (pinned: the D2H copy of a batch runs at PCIe speed)
     std::vector<frame_header> hdrs;
     size_t next = 0, have = 0;
     bool eof = false;
@@ -259,7 +259,14 @@ dbde_file_walker dbde_start_file_walk(const char *name, int frames_buffered, vid
     if (ferror(f)) { fclose(f); free(w.buffer); w.buffer = NULL; w.fptr = NULL; return w; }
     WalkerSide *s = new WalkerSide();
     s->batch = frames_buffered;
-    s->frames.resize((size_t)frames_buffered * w.width * w.height);
+    if (dbde_b200_host_alloc((size_t)frames_buffered * w.width * w.height, (void **)&s->frames) != 0) {
+        delete s;
+        fclose(f);
+        free(w.buffer);
+        w.buffer = NULL;
+        w.fptr = NULL;
+        return w;
+    }
     s->hdrs.resize(frames_buffered);
     std::lock_guard<std::mutex> lk(g_wmx);
     g_wside[w.buffer] = s;
@@ -280,7 +287,7 @@ bool dbde_walk_a_file(dbde_file_walker *w, frame_header *fh, uint8_t *image) {
         std::vector<uint32_t> status(n);
         std::vector<uint64_t> index(n);
         int rc = dbde_b200_decode_host(ctx(), w->buffer + w->i, (size_t)offs[n], offs.data(), w->width, w->height,
-                                       (int)n, s->frames.data(), status.data(), index.data());
+                                       (int)n, s->frames, status.data(), index.data());
         if (rc) die("dbde_walk_a_file", rc);
         s->have = 0;
         for (long k = 0; k < n; k++) {
@@ -295,7 +302,7 @@ bool dbde_walk_a_file(dbde_file_walker *w, frame_header *fh, uint8_t *image) {
     }
     *fh = s->hdrs[s->next];
     if (fh->u64s != 2) { dbde_end_file_walk(w); return false; }   // reference :416
-    memcpy(image, s->frames.data() + px * s->next, px);
+    memcpy(image, s->frames + px * s->next, px);
     s->next++;
     w->frames++;
     return true;
@@ -309,7 +316,11 @@ void dbde_end_file_walk(dbde_file_walker *w) {
         {
             std::lock_guard<std::mutex> lk(g_wmx);
             auto it = g_wside.find(w->buffer);
-            if (it != g_wside.end()) { delete it->second; g_wside.erase(it); }
+            if (it != g_wside.end()) {
+                if (it->second->frames) dbde_b200_host_free(it->second->frames);
+                delete it->second;
+                g_wside.erase(it);
+            }
         }
         free(w->buffer);
         w->buffer = NULL;
