@@ -18,8 +18,6 @@
 #include "dbde_device.cuh"
 #include "dbde_kernels.h"
 
-#include <cstdlib>
-
 namespace dbde {
 
 constexpr int kDecStages = 3;
@@ -445,8 +443,7 @@ cudaError_t launch_decode_scan(const DecParams &P, cudaStream_t stream) {
 }
 
 cudaError_t launch_decode(const DecParams &P, bool fast, int num_sms, cudaStream_t stream) {
-    size_t smem = dec_smem_bytes(P.g);
-    if (const char *e = getenv("DBDE_B200_DEC_PAD_SMEM")) smem += (size_t)atoi(e);   // experiment knob
+    const size_t smem = dec_smem_bytes(P.g);
     auto kern = fast ? dbde_decode_kernel<true> : dbde_decode_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -454,10 +451,6 @@ cudaError_t launch_decode(const DecParams &P, bool fast, int num_sms, cudaStream
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kDecThreads, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
-    if (const char *e = getenv("DBDE_B200_DEC_CTAS")) {      // experiment knob: cap the CTAs per SM
-        const int cap = atoi(e);
-        if (cap >= 1 && cap < occ) occ = cap;
-    }
     unsigned grid = (unsigned)(num_sms * occ);
     if (grid > P.nparts) grid = P.nparts;
     if (grid == 0) return cudaSuccess;
