@@ -4,12 +4,15 @@
 // One persistent kernel, one pass over the pixels:
 //   warp 8  (producer) : claims partitions from an atomic ticket and bulk-TMAs their pixel rows
 //                        into a ring of shared-memory stages (mbarrier full/empty pipeline)
-//   warps 0-7 (tiles)  : one lane per 8x8 tile -- min, depth = bits(max-min), bit packing; the
-//                        payload words are staged LINEARLY in the (now dead) pixel stage with
-//                        immediate-offset 8-byte stores and copied out with coalesced 16-byte stores
-//   warp 9  (scan)     : publishes the partition's depth sum, resolves its exclusive prefix with
-//                        a single-pass decoupled look-back, and hands the output address to the
-//                        tile warps; writes the frame's fixed fields (header, lengths, n64)
+//   warps 0-7 (tiles)  : one lane per 8x8 tile -- min, depth = bits(max-min), bit packing.  A tile
+//                        warp never meets the other tile warps: it hands the pixel stage back as
+//                        soon as its pixels are in registers and stages its payload words in its
+//                        OWN 2 KiB region of a double-buffered output ring (immediate-offset 8-byte
+//                        stores), then copies its run out with coalesced stores one partition later
+//   warp 9  (scan)     : sums the warps' depth totals, publishes the partition aggregate, resolves
+//                        its exclusive prefix with a single-pass decoupled look-back, and hands the
+//                        tile warps {frame, exclusive prefix, each warp's offset inside the
+//                        partition}; writes the frame's fixed fields (header, lengths, n64)
 // Word offsets are per-frame quantities (the reference zeroes n64 per frame, dbde_util.cpp:146),
 // so there is one look-back chain per frame, and tickets are INTERLEAVED across the frames of the
 // batch (ticket t -> frame t mod N, partition t div N): the partitions in flight at any moment
@@ -17,18 +20,16 @@
 // and the look-back is one descriptor read instead of a convoy of L2 round trips.  Frame f's
 // record is written to its own slot (out + f * slot_stride); sizes go to frame_sizes[].
 //
-// The kernel is issue-bound before it is HBM-bound (ncu: ~75 % issue-slot utilisation), so the
-// tile warps' loop is written for instruction count: no staging swizzle (a tile's k words go to
-// stage + 8*offset + {0, 8, 16, ...}), one 16-byte control read per partition, a REDUX for the
-// cross-warp prefix, and a copy-out that only distinguishes the parity of the first word.
+// The kernel is issue/latency-bound before it is HBM-bound (ncu: ~72 % issue-slot utilisation with
+// 7.5 warps per scheduler), so the tile warps' loop is written for instruction count and for
+// independence: no staging swizzle, one 16-byte control read per partition, no CTA-wide barrier
+// (the in-place staging of the first versions needed one per partition: 12 % of the stall samples).
 #include "dbde_device.cuh"
 #include "dbde_kernels.h"
 
 namespace dbde {
 
-// 4 stages x 16 KiB x 3 CTAs/SM fill the 227 KiB of shared memory; measured on micro-2048: 3 stages
-// -7 %, 5-6 stages at 2 CTAs/SM -19 %, releasing the deferred stage half an iteration earlier -1 %.
-constexpr int kEncStages = 4;
+constexpr int kEncRing = 4;        // bookkeeping slots (aggregates, bases): a tile warp is <= 2 partitions ahead of the scan warp
 constexpr int kEncThreads = kTilesPerPart + 64;
 
 struct alignas(16) EncCtl {     // per-stage control block, written by the producer warp
@@ -47,53 +48,12 @@ struct alignas(16) EncBase {    // per-stage, written by the scan warp
 };
 
 struct EncSmem {
-    uint64_t full[kEncStages], empty[kEncStages], aggbar[kEncStages], basebar[kEncStages];
-    EncCtl ctl[kEncStages];
-    EncBase base[kEncStages];
-    uint32_t warptot[kEncStages][kConsumerWarps];   // depth sum of each tile warp
+    uint64_t full[kEncRing], empty[kEncRing], aggbar[kEncRing], basebar[kEncRing];
+    EncCtl ctl[kEncRing];
+    EncBase base[kEncRing];
+    uint32_t warptot[kEncRing][kConsumerWarps];   // depth sum of each tile warp
+    uint32_t wbase[kEncRing][kConsumerWarps];       // its word offset inside the partition (scan warp)
 };
-
-// Copy `n` staged U64 words (linear at `stage`) to global memory at `dst`; thread `me` of 256.
-__device__ __forceinline__ void enc_copy_out(const uint8_t *stage, uint8_t *dst, uint32_t n, uint32_t me) {
-    const uintptr_t ga = (uintptr_t)dst;
-    if ((ga & 7) == 0) {
-        // 16-byte stores over the aligned middle, one 8-byte word at either end if needed
-        const uint32_t head = (uint32_t)(ga >> 3) & 1u;
-        if (n <= head) {
-            if (n && me == 0) st_stream_u64(dst, *reinterpret_cast<const uint64_t *>(stage));
-            return;
-        }
-        const uint32_t npair = (n - head) >> 1;                 // <= 1024: at most four rounds of 256 threads
-        const uint8_t *sp = stage + 8 * head + 16 * me;
-        uint8_t *dp = dst + 8 * head + 16 * me;
-        if (head == 0) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (j * kTilesPerPart >= npair) break;
-                if (me + j * kTilesPerPart < npair)
-                    st_stream_v4u32(dp + 16 * kTilesPerPart * j, *reinterpret_cast<const uint4 *>(sp + 16 * kTilesPerPart * j));
-            }
-        } else {
-            if (me == 0) st_stream_u64(dst, *reinterpret_cast<const uint64_t *>(stage));
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (j * kTilesPerPart >= npair) break;
-                if (me + j * kTilesPerPart < npair) {
-                    const uint2 a = *reinterpret_cast<const uint2 *>(sp + 16 * kTilesPerPart * j);
-                    const uint2 b = *reinterpret_cast<const uint2 *>(sp + 16 * kTilesPerPart * j + 8);
-                    st_stream_v4u32(dp + 16 * kTilesPerPart * j, make_uint4(a.x, a.y, b.x, b.y));
-                }
-            }
-        }
-        const uint32_t done = head + 2 * npair;
-        if (done < n && me == 32) st_stream_u64(dst + 8 * (size_t)done, *reinterpret_cast<const uint64_t *>(stage + 8 * done));
-    } else if ((ga & 3) == 0) {
-        for (uint32_t i = me; i < 2 * n; i += kTilesPerPart)
-            st_stream_u32(dst + 4 * (size_t)i, *reinterpret_cast<const uint32_t *>(stage + 4 * i));
-    } else {
-        for (uint32_t i = me; i < 8 * n; i += kTilesPerPart) dst[i] = stage[i];
-    }
-}
 
 // depth 8: the words are the (p - min) rows themselves (dbde_util.cpp:57-64).  Equal-depth
 // neighbours sit 64 bytes apart -- an 8-way bank conflict for 8-byte stores -- so the 64 bytes go
@@ -112,11 +72,15 @@ __device__ __forceinline__ void enc_store_depth8(const uint32_t (&w)[16], uint8_
     }
 }
 
+// Shared memory per CTA: 2 pixel stages x 16 KiB + 2 x 8 x 2 KiB of output ring = 66 KiB -> 3 CTAs/SM.
+// (The in-place design held 4 x 16 KiB; there 3 stages cost 7 % and 5-6 stages at 2 CTAs/SM 19 %.)
+constexpr int kEncStages = 2;                                  // pixel stages (handed back as soon as the pixels are in registers)
+constexpr int kEncWarpBytes = 64 * 32 + 16;                     // a warp's private staging region: worst case 32 tiles x 64 bytes
+constexpr int kWidePitch = 8 * kTilesPerPart;
 // FAST : 16-byte aligned rows, no partial tiles (W % 16 == 0, H % 8 == 0).
 // WIDE : FAST and w % 256 == 0 (2048-, 4096-pixel-wide frames): every partition is one full 256-tile
 //        band segment, so the smem pitch is the constant 2048 (immediate-offset row loads) and no
 //        lane is ever idle.
-constexpr int kWidePitch = 8 * kTilesPerPart;
 template <bool FAST, bool WIDE>
 __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -124,11 +88,13 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
     uint8_t *stages = smem_raw + ((sizeof(EncSmem) + 127) & ~127);
     const PartGeom &g = P.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // warp-private output ring: out[2][8 warps][kEncWarpBytes], after the kEncStages input stages
+    uint8_t *outring = stages + (size_t)kEncStages * g.stage_bytes;
 
     if (tid == 0) {
-        for (int s = 0; s < kEncStages; s++) {
+        for (int s = 0; s < kEncRing; s++) {
             mbar_init(&S.full[s], 1);
-            mbar_init(&S.empty[s], kConsumerWarps);
+            mbar_init(&S.empty[s], kConsumerWarps + 1);       // the eight tile warps and the scan warp
             mbar_init(&S.aggbar[s], kConsumerWarps);
             mbar_init(&S.basebar[s], 1);
         }
@@ -210,16 +176,20 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
     } else if (warp == kConsumerWarps + 1) {
         // ============================ scan warp ============================
         for (unsigned it = 0;; it++) {
-            const int s = it % kEncStages;
-            const uint32_t ph = (it / kEncStages) & 1;
-            mbar_wait_sleepy(&S.full[s], ph);
+            const int s = it % kEncStages, ss = it % kEncRing;
+            mbar_wait_sleepy(&S.full[s], (it / kEncStages) & 1);
             const int4 c0 = *reinterpret_cast<const int4 *>(&S.ctl[s].part);
+            const int q = S.ctl[s].q;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.empty[s]);          // the control block has been read
             if (c0.x < 0) break;
             const unsigned p = (unsigned)c0.x;
-            const int f = c0.y, q = S.ctl[s].q;
-            mbar_wait_sleepy(&S.aggbar[s], ph);
-            const uint32_t wt = lane < kConsumerWarps ? S.warptot[s][lane] : 0u;
-            const uint64_t agg = __reduce_add_sync(0xffffffffu, wt);
+            const int f = c0.y;
+            mbar_wait_sleepy(&S.aggbar[ss], (it / kEncRing) & 1);
+            const uint32_t wt = lane < kConsumerWarps ? S.warptot[ss][lane] : 0u;
+            const uint32_t winc = warp_inclusive_scan(wt, lane);
+            const uint64_t agg = __shfl_sync(0xffffffffu, winc, kConsumerWarps - 1);
+            if (lane < kConsumerWarps) S.wbase[ss][lane] = winc - wt;      // each tile warp's offset inside the partition
             uint64_t excl = 0;                      // U64 words of this frame before this partition
             if (q == 0) {
                 if (lane == 0) st_relaxed_u64(P.desc + p, desc_make(kDescPrefix, agg));
@@ -230,10 +200,11 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
             }
             const size_t fixed = 32 + 2 * (size_t)g.wh;     // frame header + lengths + planes
             uint8_t *frame = P.out + (size_t)f * P.slot_stride;
+            __syncwarp();
             if (lane == 0) {
-                S.base[s].frame = frame;
-                *reinterpret_cast<uint2 *>(&S.base[s].excl) = make_uint2((uint32_t)excl, (uint32_t)agg);
-                mbar_arrive(&S.basebar[s]);
+                S.base[ss].frame = frame;
+                *reinterpret_cast<uint2 *>(&S.base[ss].excl) = make_uint2((uint32_t)excl, (uint32_t)agg);
+                mbar_arrive(&S.basebar[ss]);
             }
             if (q == g.ppf - 1) {
                 // last partition of the frame: the fixed fields (dbde_util.cpp:141-146,182-188,191)
@@ -265,35 +236,42 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
         }
         const uint32_t toff = (uint32_t)(sb * 8) * (uint32_t)g.pitch + (uint32_t)stx * 8u;   // my tile inside a stage
         const size_t fixed = 32 + 2 * (size_t)g.wh;
-        // deferred partition (iteration it-1): its depth/min stay in registers until its addresses
-        // are known.  d_km = depth | min << 8 | valid << 16.
-        uint32_t d_km = 0;
+        // deferred partition (iteration it-1): its depth/min/word count stay in registers until its
+        // addresses are known.  d_km = depth | min << 8 | valid << 16.
+        uint32_t d_km = 0, d_wtot = 0;
         int d_tfirst = 0;
 
         auto flush_deferred = [&](unsigned dit) {
-            const int ds = dit % kEncStages;
-            const uint8_t *stage = stages + (size_t)ds * g.stage_bytes;
-            mbar_wait(&S.basebar[ds], (dit / kEncStages) & 1);
+            const int ds = dit % kEncRing;
+            const uint8_t *src = outring + ((size_t)(dit & 1) * kConsumerWarps + warp) * kEncWarpBytes;
+            mbar_wait(&S.basebar[ds], (dit / kEncRing) & 1);
             const uint4 b = *reinterpret_cast<const uint4 *>(&S.base[ds]);
             uint8_t *frame = reinterpret_cast<uint8_t *>(((uint64_t)b.y << 32) | b.x);
             // ---- depth and minimum planes (dbde_util.cpp:156-157)
-            if (d_km >> 16) {
+            if (WIDE || (d_km >> 16)) {
                 uint8_t *pl = frame + d_tfirst + tid;
                 pl[24] = (uint8_t)d_km;
                 pl[28 + (size_t)g.wh] = (uint8_t)(d_km >> 8);
             }
-            // ---- coalesced copy-out of the partition's words, by all tile warps
-            enc_copy_out(stage, frame + fixed + 8 * (size_t)b.z, b.w, (uint32_t)tid);
-            fence_proxy_async();        // my generic accesses to the stage precede the next TMA fill
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.empty[ds]);
+            // ---- this warp's words, by this warp: one coalesced run per warp
+            uint8_t *dst = frame + fixed + 8 * ((size_t)b.z + S.wbase[ds][warp]);
+            const uint32_t n = d_wtot;
+            if (((uintptr_t)dst & 7) == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    if (32u * j >= n) break;
+                    if (lane + 32u * j < n)
+                        st_stream_u64(dst + 8 * (lane + 32 * j), *reinterpret_cast<const uint64_t *>(src + 8 * (lane + 32 * j)));
+                }
+            } else {
+                for (uint32_t i = lane; i < 8 * n; i += 32) dst[i] = src[i];
+            }
         };
 
         unsigned it = 0;
         for (;; it++) {
-            const int s = it % kEncStages;
-            const uint32_t ph = (it / kEncStages) & 1;
-            mbar_wait(&S.full[s], ph);
+            const int s = it % kEncStages, ss = it % kEncRing;
+            mbar_wait(&S.full[s], (it / kEncStages) & 1);
             const int4 c0 = *reinterpret_cast<const int4 *>(&S.ctl[s].part);   // part, f, tfirst, nt
             if (c0.x < 0) break;
             uint8_t *stage = stages + (size_t)s * g.stage_bytes;
@@ -342,6 +320,10 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
                     px[2 * r + 1] = v.y;
                 }
             }
+            // the pixels are in registers: hand the stage back to the producer right away
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.empty[s]);
             // ---- stage (2): min, depth
             uint32_t mn = tile_min(px);
             int k = tile_subtract_depth(px, mn);
@@ -349,22 +331,19 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
             // ---- stage (3a): depth sums -> scan warp
             const uint32_t incl = warp_inclusive_scan((uint32_t)k, lane);
             if (lane == 31) {
-                S.warptot[s][warp] = incl;
-                mbar_arrive(&S.aggbar[s]);
+                S.warptot[ss][warp] = incl;
+                mbar_arrive(&S.aggbar[ss]);
             }
-            // every tile of this partition is in registers (its stage may be overwritten) and every
-            // payload word of the deferred partition has been staged (it may be copied out)
-            bar_consumers();
-            // word offset of my tile inside the partition: lower warps' totals (REDUX) + my warp's prefix
-            const uint32_t wt = lane < warp ? S.warptot[s][lane & (kConsumerWarps - 1)] : 0u;
-            const uint32_t off = __reduce_add_sync(0xffffffffu, wt) + incl - (uint32_t)k;
+            // my tile's word offset inside this WARP's private staging region: no other warp is involved
+            const uint32_t off = incl - (uint32_t)k;
+            uint8_t *stage_out = outring + ((size_t)(it & 1) * kConsumerWarps + warp) * kEncWarpBytes;
             // ---- stage (4): pack (p - min) into k U64 words, staged linearly in the dead pixel bytes
             if (k > 0) {
                 const uint32_t c1 = (1u << k) - 256u, c2 = (1u << (2 * k)) - 65536u;
                 uint32_t q[16];
 #pragma unroll
                 for (int i = 0; i < 16; i++) q[i] = squeeze4(px[i], c1, c2);
-                uint2 *wp = reinterpret_cast<uint2 *>(stage + 8 * off);
+                uint2 *wp = reinterpret_cast<uint2 *>(stage_out + 8 * off);
                 auto store = [&](int n, uint32_t lo, uint32_t hi) { wp[n] = make_uint2(lo, hi); };
                 switch (k) {
                     case 1: concat_fields<1>(q, store); break;
@@ -374,17 +353,16 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
                     case 5: concat_fields<5>(q, store); break;
                     case 6: concat_fields<6>(q, store); break;
                     case 7: concat_fields<7>(q, store); break;
-                    default: enc_store_depth8(q, stage + 8 * off, off); break;   // squeeze4 is the identity at depth 8
+                    default: enc_store_depth8(q, stage_out + 8 * off, off); break;   // squeeze4 is the identity at depth 8
                 }
             }
+            __syncwarp();               // the warp's words are staged before any lane copies them out
             if (it > 0) flush_deferred(it - 1);
             d_km = (uint32_t)k | (mn << 8) | ((uint32_t)valid << 16);
+            d_wtot = __shfl_sync(0xffffffffu, incl, 31);
             d_tfirst = c0.z;
         }
-        if (it > 0) {
-            bar_consumers();            // the last partition's payload is fully staged
-            flush_deferred(it - 1);
-        }
+        if (it > 0) flush_deferred(it - 1);
     }
 }
 
@@ -423,7 +401,7 @@ cudaError_t launch_compact(const uint8_t *slots, uint64_t slot_stride, const uin
 }
 
 size_t enc_smem_bytes(const PartGeom &g) {
-    return ((sizeof(EncSmem) + 127) & ~(size_t)127) + (size_t)kEncStages * g.stage_bytes;
+    return ((sizeof(EncSmem) + 127) & ~(size_t)127) + (size_t)kEncStages * g.stage_bytes + 2 * (size_t)kConsumerWarps * kEncWarpBytes;
 }
 
 cudaError_t launch_encode(const EncParams &P, bool fast, int num_sms, cudaStream_t stream) {
