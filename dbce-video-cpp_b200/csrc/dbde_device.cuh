@@ -156,6 +156,13 @@ __device__ __forceinline__ uint64_t desc_make(uint64_t status, uint64_t value) {
 // predecessors (with frame-interleaved tickets the nearest one is normally already resolved);
 // later rounds read 128 at a time with four independent loads per lane.
 constexpr int kLookbackSub = 4;
+constexpr uint64_t kLookbackNotReady = ~0ull;
+// WAIT = true : spins until every needed predecessor has published something (the classic look-back).
+// WAIT = false: one opportunistic pass -- returns kLookbackNotReady as soon as it meets an unpublished
+//               descriptor.  The exclusive prefix does not depend on the caller's own aggregate, so
+//               the scan warp can take it BEFORE its partition's depth sums exist; with
+//               frame-interleaved tickets the predecessors are long finished and this succeeds.
+template <bool WAIT>
 __device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t *desc, unsigned p, unsigned first, int lane) {
     uint64_t sum = 0;
     long long look = (long long)p - 1;
@@ -190,6 +197,7 @@ __device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t *desc, uns
             }
         }
         if (done) return sum;
+        if (!WAIT && stall) return kLookbackNotReady;
         look -= 32 * consumed;                           // fully aggregated sub-windows are never re-read
         nsub = kLookbackSub;
     }

@@ -105,13 +105,17 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
     if (warp == kConsumerWarps) {
         // ============================ producer warp ============================
         const size_t fbytes = (size_t)g.W * g.H;
+        // The ticket for the NEXT partition is claimed one iteration early, so the atomic's L2 round
+        // trip overlaps the wait for a free stage instead of delaying the refill (with two stages the
+        // refill latency is the budget).  A claimed ticket is always processed next: progress holds.
+        unsigned t_next = 0;
+        if (lane == 0) t_next = atomicAdd(P.ticket, 1u);
         for (unsigned it = 0;; it++) {
             const int s = it % kEncStages;
             const uint32_t ph = (it / kEncStages) & 1;
+            unsigned t = __shfl_sync(0xffffffffu, t_next, 0);
+            if (lane == 0 && t < P.nparts) t_next = atomicAdd(P.ticket, 1u);
             mbar_wait_sleepy(&S.empty[s], ph ^ 1);
-            unsigned t = 0;
-            if (lane == 0) t = atomicAdd(P.ticket, 1u);
-            t = __shfl_sync(0xffffffffu, t, 0);
             // frame-interleaved order: all frames' partition 0, then all frames' partition 1, ...
             const unsigned tq = t / (unsigned)P.nframes;
             const unsigned p = (t - tq * (unsigned)P.nframes) * (unsigned)g.ppf + tq;
@@ -185,19 +189,21 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
             if (c0.x < 0) break;
             const unsigned p = (unsigned)c0.x;
             const int f = c0.y;
+            // The exclusive prefix only needs the PREDECESSORS' descriptors: take it while the tile warps
+            // are still computing this partition's depths, so that nothing but a shared-memory hand-off
+            // stands between their last arrival and the base they wait for at copy-out time.
+            uint64_t excl = q == 0 ? 0ull : lookback_exclusive<false>(P.desc, p, p - (unsigned)q, lane);
             mbar_wait_sleepy(&S.aggbar[ss], (it / kEncRing) & 1);
             const uint32_t wt = lane < kConsumerWarps ? S.warptot[ss][lane] : 0u;
             const uint32_t winc = warp_inclusive_scan(wt, lane);
             const uint64_t agg = __shfl_sync(0xffffffffu, winc, kConsumerWarps - 1);
             if (lane < kConsumerWarps) S.wbase[ss][lane] = winc - wt;      // each tile warp's offset inside the partition
-            uint64_t excl = 0;                      // U64 words of this frame before this partition
-            if (q == 0) {
-                if (lane == 0) st_relaxed_u64(P.desc + p, desc_make(kDescPrefix, agg));
-            } else {
+            if (excl == kLookbackNotReady) {
+                // a predecessor is still in flight (few frames in the batch): the classic protocol
                 if (lane == 0) st_relaxed_u64(P.desc + p, desc_make(kDescAggregate, agg));
-                excl = lookback_exclusive(P.desc, p, p - (unsigned)q, lane);
-                if (lane == 0) st_relaxed_u64(P.desc + p, desc_make(kDescPrefix, excl + agg));
+                excl = lookback_exclusive<true>(P.desc, p, p - (unsigned)q, lane);
             }
+            if (lane == 0) st_relaxed_u64(P.desc + p, desc_make(kDescPrefix, excl + agg));
             const size_t fixed = 32 + 2 * (size_t)g.wh;     // frame header + lengths + planes
             uint8_t *frame = P.out + (size_t)f * P.slot_stride;
             __syncwarp();
