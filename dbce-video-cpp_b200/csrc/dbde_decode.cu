@@ -71,10 +71,36 @@ __global__ void __launch_bounds__(256) dbde_decode_scan_kernel(const DecParams P
     // reduced so four global loads are in flight per lane.
     const uint8_t *dp = rec + 24;
     bool big = false;
-#ifndef DBDE_SCAN_BATCH
-#define DBDE_SCAN_BATCH 4
-#endif
-    constexpr int kBatch = DBDE_SCAN_BATCH;
+    if (g.wh == kTilesPerPart * g.ppf && (((uintptr_t)dp) & 7) == 0) {
+        // Every partition is a full run of 256 tiles starting at tile 256*q and the plane is 8-byte
+        // aligned (the usual case): no geometry, no edge handling -- one 8-byte load per lane per
+        // partition, eight independent partitions in flight per warp.
+        constexpr int kFastBatch = 8;
+        for (int q0 = warp * kFastBatch; q0 < g.ppf; q0 += 8 * kFastBatch) {
+            uint2 v[kFastBatch];
+#pragma unroll
+            for (int b = 0; b < kFastBatch; b++)
+                v[b] = q0 + b < g.ppf ? *reinterpret_cast<const uint2 *>(dp + (size_t)kTilesPerPart * (q0 + b) + 8 * lane)
+                                      : make_uint2(0u, 0u);
+#pragma unroll
+            for (int b = 0; b < kFastBatch; b++) {
+                const uint32_t over = ((((v[b].x & 0x7f7f7f7fu) + 0x77777777u) | v[b].x) |
+                                       (((v[b].y & 0x7f7f7f7fu) + 0x77777777u) | v[b].y)) & 0x80808080u;
+                uint32_t sum;
+                if (over) {                                          // rare: clamp byte-wise like the general path
+                    big = true;
+                    sum = 0;
+                    for (int i = 0; i < 4; i++) sum += min((v[b].x >> (8 * i)) & 0xffu, 8u) + min((v[b].y >> (8 * i)) & 0xffu, 8u);
+                } else {
+                    sum = __dp4a(v[b].x, 0x01010101u, __dp4a(v[b].y, 0x01010101u, 0u));
+                }
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                if (q0 + b < g.ppf && (lane & 3) == 0) wp[(q0 + b) * kConsumerWarps + (lane >> 2)] = sum;
+            }
+        }
+    } else {
+    constexpr int kBatch = 4;
     for (int q0 = warp * kBatch; q0 < g.ppf; q0 += 8 * kBatch) {
         uint32_t lo[kBatch], hi[kBatch];
 #pragma unroll
@@ -117,6 +143,7 @@ __global__ void __launch_bounds__(256) dbde_decode_scan_kernel(const DecParams P
             sum += __shfl_xor_sync(0xffffffffu, sum, 2);
             if (q < g.ppf && (lane & 3) == 0) wp[q * kConsumerWarps + (lane >> 2)] = sum;
         }
+    }
     }
     if (big) atomicOr(&s_flag, 1u);
     __syncthreads();
