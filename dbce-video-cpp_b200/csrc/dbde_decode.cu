@@ -201,10 +201,13 @@ struct alignas(16) DecCtl {
     int y0, tx0, ntx, pad1;    // first band / first tile column / tile columns (generic path)
     uint32_t wbase[kConsumerWarps];   // word offset of each tile warp inside the partition's payload
 };
-struct DecSmem {
-    uint64_t full[kDecStages], empty[kDecStages];
-    DecCtl ctl[kDecStages];
+template <int NSTAGES>
+struct DecSmemT {
+    uint64_t full[NSTAGES], empty[NSTAGES];
+    uint64_t outfull[2], outempty[2];      // staged-store kernel only
+    DecCtl ctl[NSTAGES];
 };
+using DecSmem = DecSmemT<kDecStages>;
 
 // ALIGN = 8: payload words are 8-byte aligned in shared memory (LDS.64), 4: 4-byte aligned
 // (LDS.32), 1: any byte offset (funnel-shifted pairs).  Uniform per partition.
@@ -283,6 +286,133 @@ __device__ __forceinline__ void store_row_generic(uint8_t *rp, uint64_t x, int n
     if (last_in_run && a + (uint32_t)ncol > 8u) store_partial(q + 8, x >> (64u - sh), 0u, a + (uint32_t)ncol - 8u);
 }
 
+// ------------------------------------------------------------------ one lane == one tile: payload -> pixels
+// Reads the tile's depth and minimum from the staged planes and its k words from the staged payload,
+// returns the 64 pixels (+min applied) in px.  Warp-wide call (scan + vote).
+#ifndef DBDE_VAR_MIN_DEPTHS
+#define DBDE_VAR_MIN_DEPTHS 3
+#endif
+__device__ __forceinline__ void dec_unpack_tile(const uint8_t *stage, const uint4 &c1, uint32_t wbase, int tid, int lane,
+                                                bool valid, uint32_t (&px)[16]) {
+    const uint32_t pres = c1.x;
+    int k = 0;
+    uint32_t mn = 0;
+    if (valid) {
+        k = stage[kDecPayloadBytes + c1.y + tid];
+        mn = stage[kDecPayloadBytes + kDecPlaneBytes + c1.z + tid];
+    }
+    const uint32_t incl = warp_inclusive_scan((uint32_t)k, lane);
+    const uint32_t woff = wbase + incl - (uint32_t)k;
+    const uint32_t m4 = mn * 0x01010101u;
+    // how many different non-zero depths does this warp hold?  Each one is a pass through its own
+    // specialisation; from DBDE_VAR_MIN_DEPTHS on, the depth-agnostic row unpacker is shorter.
+    const uint32_t kinds = __reduce_or_sync(0xffffffffu, (1u << k) >> 1);
+    const uint8_t *pay = stage + pres + 8 * (size_t)woff;
+    if (__popc(kinds) >= DBDE_VAR_MIN_DEPTHS) {
+        if (k > 0) {
+            unpack_rows_var(pay, k, px, m4);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) px[i] = m4;
+        }
+    } else if (k > 0) {
+        uint32_t q[16];
+        if ((pres & 7u) == 0) load_split_any<8>(k, pay, q);     // the usual case: records on 8-byte boundaries
+        else load_split_any<1>(k, pay, q);
+        const uint32_t c1n = 256u - (1u << k), c2n = 65536u - (1u << (2 * k));
+        const uint32_t kmask2 = ((1u << k) - 1u) * 0x00010001u;
+#pragma unroll
+        for (int i = 0; i < 16; i++) px[i] = spread4(q[i], k, c1n, c2n, kmask2) + m4;   // +min (dbde_util.cpp:246)
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) px[i] = m4;                                        // depth 0 (dbde_util.cpp:218-226)
+    }
+}
+
+// ------------------------------------------------------------------ producer warp (both unpack kernels)
+// INFLIGHT: payload bytes the producer lets a CTA have in flight (adaptive depth), see kDecInflightBytes.
+template <int NSTAGES, uint32_t INFLIGHT>
+__device__ __forceinline__ void dec_producer(const DecParams &P, DecSmemT<NSTAGES> &S, uint8_t *stages, int lane) {
+    const PartGeom &g = P.g;
+    const int nitems = g.ppf * kConsumerWarps;
+    // ============================ producer warp ============================
+    // static round-robin: nothing waits on another CTA here, so no ticket is needed and the
+    // next partition's bookkeeping loads can be issued one iteration early
+    unsigned p = blockIdx.x;
+    uint32_t nx_status = 0, nx_v = 0;
+    uint64_t nx_off = 0;
+    auto prefetch = [&](unsigned pp) {
+        if (pp < P.nparts) {
+            const PartInfo pi = part_info(g, pp);
+            nx_status = P.status[pi.f];
+            nx_off = P.frame_offsets[pi.f];
+            nx_v = lane <= kConsumerWarps ? P.wprefix[(size_t)pi.f * (nitems + 1) + pi.q * kConsumerWarps + lane] : 0u;
+        }
+    };
+    prefetch(p);
+    uint32_t b1 = 0, b2 = 0;                   // payload bytes of the two previous iterations
+    for (unsigned it = 0;; it++, p += gridDim.x) {
+        const int s = it % NSTAGES;
+        const uint32_t ph = (it / NSTAGES) & 1;
+        const uint32_t status = nx_status, v = nx_v;
+        const uint64_t off = nx_off;
+        prefetch(p + gridDim.x);
+        mbar_wait_sleepy(&S.empty[s], ph ^ 1);
+        if (p >= P.nparts) {
+            if (lane == 0) {
+                S.ctl[s].part = -1;
+                mbar_arrive(&S.full[s]);
+            }
+            break;
+        }
+        if (status != 0) {
+            if (lane == 0) {
+                *reinterpret_cast<int2 *>(&S.ctl[s].part) = make_int2((int)p, 1);
+                mbar_arrive(&S.full[s]);
+            }
+            b2 = b1;
+            b1 = 0;
+            continue;
+        }
+        const PartInfo pi = part_info(g, p);
+        const uint8_t *rec = P.stream + off;
+        const uint32_t v0 = __shfl_sync(0xffffffffu, v, 0), v8 = __shfl_sync(0xffffffffu, v, kConsumerWarps);
+        const uint32_t agg = v8 - v0;
+        // adaptive depth: with large payloads, wait until the partition issued two iterations ago
+        // has been consumed (at most two in flight) before adding this one
+        if (NSTAGES > 2 && it >= 2 && 8u * agg + b1 + b2 > INFLIGHT)
+            mbar_wait_sleepy(&S.empty[(it - 2) % NSTAGES], ((it - 2) / NSTAGES) & 1);
+        b2 = b1;
+        b1 = 8u * agg;
+        uint8_t *stage = stages + (size_t)s * kDecStageBytes;
+        // lane 0: payload words, lane 1: depth bytes, lane 2: minimum bytes (16-byte hulls)
+        const uint8_t *src = nullptr;
+        uint32_t nbytes = 0;
+        uint8_t *dst = stage;
+        if (lane == 0) { src = rec + 32 + 2 * (size_t)g.wh + 8ull * v0; nbytes = 8 * agg; }
+        if (lane == 1) { src = rec + 24 + pi.tfirst; nbytes = (uint32_t)pi.nt; dst = stage + kDecPayloadBytes; }
+        if (lane == 2) { src = rec + 28 + (size_t)g.wh + pi.tfirst; nbytes = (uint32_t)pi.nt; dst = stage + kDecPayloadBytes + kDecPlaneBytes; }
+        const uintptr_t a0 = (uintptr_t)src & ~(uintptr_t)15;
+        const uintptr_t a1 = ((uintptr_t)src + nbytes + 15) & ~(uintptr_t)15;
+        const uint32_t len = nbytes ? (uint32_t)(a1 - a0) : 0u;
+        const uint32_t res = (uint32_t)((uintptr_t)src - a0);
+        if (lane < kConsumerWarps) S.ctl[s].wbase[lane] = v - v0;
+        // lanes 0..2 hold the three residuals: gather them so lane 0 writes the block with two 16-byte stores
+        const uint32_t kres = __shfl_sync(0xffffffffu, res, 1), mres = __shfl_sync(0xffffffffu, res, 2);
+        if (lane == 0) {
+            *reinterpret_cast<int4 *>(&S.ctl[s].part) = make_int4((int)p, 0, pi.f, pi.nt);
+            *reinterpret_cast<uint4 *>(&S.ctl[s].pres) =
+                make_uint4(res, kres, mres, (uint32_t)(8 * pi.y0) * (uint32_t)g.W + 8u * (uint32_t)pi.tx0);
+            *reinterpret_cast<int4 *>(&S.ctl[s].y0) = make_int4(pi.y0, pi.tx0, pi.ntx, 0);
+        }
+        const uint32_t total = __reduce_add_sync(0xffffffffu, lane < 3 ? len : 0u);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_expect_tx(&S.full[s], total);
+        __syncwarp();
+        if (lane < 3 && len) tma_load_1d(dst, (const void *)a0, len, &S.full[s]);
+    }
+}
+
 template <bool FAST>
 __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -291,7 +421,6 @@ __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecPa
     const PartGeom &g = P.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const size_t fbytes = (size_t)g.W * g.H;
-    const int nitems = g.ppf * kConsumerWarps;
 
     if (tid == 0) {
         for (int s = 0; s < kDecStages; s++) {
@@ -303,82 +432,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecPa
     __syncthreads();
 
     if (warp == kConsumerWarps) {
-        // ============================ producer warp ============================
-        // static round-robin: nothing waits on another CTA here, so no ticket is needed and the
-        // next partition's bookkeeping loads can be issued one iteration early
-        unsigned p = blockIdx.x;
-        uint32_t nx_status = 0, nx_v = 0;
-        uint64_t nx_off = 0;
-        auto prefetch = [&](unsigned pp) {
-            if (pp < P.nparts) {
-                const PartInfo pi = part_info(g, pp);
-                nx_status = P.status[pi.f];
-                nx_off = P.frame_offsets[pi.f];
-                nx_v = lane <= kConsumerWarps ? P.wprefix[(size_t)pi.f * (nitems + 1) + pi.q * kConsumerWarps + lane] : 0u;
-            }
-        };
-        prefetch(p);
-        uint32_t b1 = 0, b2 = 0;                   // payload bytes of the two previous iterations
-        for (unsigned it = 0;; it++, p += gridDim.x) {
-            const int s = it % kDecStages;
-            const uint32_t ph = (it / kDecStages) & 1;
-            const uint32_t status = nx_status, v = nx_v;
-            const uint64_t off = nx_off;
-            prefetch(p + gridDim.x);
-            mbar_wait_sleepy(&S.empty[s], ph ^ 1);
-            if (p >= P.nparts) {
-                if (lane == 0) {
-                    S.ctl[s].part = -1;
-                    mbar_arrive(&S.full[s]);
-                }
-                break;
-            }
-            if (status != 0) {
-                if (lane == 0) {
-                    *reinterpret_cast<int2 *>(&S.ctl[s].part) = make_int2((int)p, 1);
-                    mbar_arrive(&S.full[s]);
-                }
-                b2 = b1;
-                b1 = 0;
-                continue;
-            }
-            const PartInfo pi = part_info(g, p);
-            const uint8_t *rec = P.stream + off;
-            const uint32_t v0 = __shfl_sync(0xffffffffu, v, 0), v8 = __shfl_sync(0xffffffffu, v, kConsumerWarps);
-            const uint32_t agg = v8 - v0;
-            // adaptive depth: with large payloads, wait until the partition issued two iterations ago
-            // has been consumed (at most two in flight) before adding this one
-            if (kDecStages > 2 && it >= 2 && 8u * agg + b1 + b2 > kDecInflightBytes)
-                mbar_wait_sleepy(&S.empty[(it - 2) % kDecStages], ((it - 2) / kDecStages) & 1);
-            b2 = b1;
-            b1 = 8u * agg;
-            uint8_t *stage = stages + (size_t)s * kDecStageBytes;
-            // lane 0: payload words, lane 1: depth bytes, lane 2: minimum bytes (16-byte hulls)
-            const uint8_t *src = nullptr;
-            uint32_t nbytes = 0;
-            uint8_t *dst = stage;
-            if (lane == 0) { src = rec + 32 + 2 * (size_t)g.wh + 8ull * v0; nbytes = 8 * agg; }
-            if (lane == 1) { src = rec + 24 + pi.tfirst; nbytes = (uint32_t)pi.nt; dst = stage + kDecPayloadBytes; }
-            if (lane == 2) { src = rec + 28 + (size_t)g.wh + pi.tfirst; nbytes = (uint32_t)pi.nt; dst = stage + kDecPayloadBytes + kDecPlaneBytes; }
-            const uintptr_t a0 = (uintptr_t)src & ~(uintptr_t)15;
-            const uintptr_t a1 = ((uintptr_t)src + nbytes + 15) & ~(uintptr_t)15;
-            const uint32_t len = nbytes ? (uint32_t)(a1 - a0) : 0u;
-            const uint32_t res = (uint32_t)((uintptr_t)src - a0);
-            if (lane < kConsumerWarps) S.ctl[s].wbase[lane] = v - v0;
-            // lanes 0..2 hold the three residuals: gather them so lane 0 writes the block with two 16-byte stores
-            const uint32_t kres = __shfl_sync(0xffffffffu, res, 1), mres = __shfl_sync(0xffffffffu, res, 2);
-            if (lane == 0) {
-                *reinterpret_cast<int4 *>(&S.ctl[s].part) = make_int4((int)p, 0, pi.f, pi.nt);
-                *reinterpret_cast<uint4 *>(&S.ctl[s].pres) =
-                    make_uint4(res, kres, mres, (uint32_t)(8 * pi.y0) * (uint32_t)g.W + 8u * (uint32_t)pi.tx0);
-                *reinterpret_cast<int4 *>(&S.ctl[s].y0) = make_int4(pi.y0, pi.tx0, pi.ntx, 0);
-            }
-            const uint32_t total = __reduce_add_sync(0xffffffffu, lane < 3 ? len : 0u);
-            __syncwarp();
-            if (lane == 0) mbar_arrive_expect_tx(&S.full[s], total);
-            __syncwarp();
-            if (lane < 3 && len) tma_load_1d(dst, (const void *)a0, len, &S.full[s]);
-        }
+        dec_producer<kDecStages, kDecInflightBytes>(P, S, stages, lane);
     } else {
         // ============================ tile warps: one lane == one 8x8 tile ============================
         int sb = 0, stx = tid;
@@ -402,30 +456,8 @@ __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecPa
             const uint4 c1 = *reinterpret_cast<const uint4 *>(&S.ctl[s].pres);    // pres, kres, mres, pixoff
             const uint8_t *stage = stages + (size_t)s * kDecStageBytes;
             const bool valid = tid < c0.w;
-            const uint32_t pres = c1.x;
-            int k = 0;
-            uint32_t mn = 0;
-            if (valid) {
-                k = stage[kDecPayloadBytes + c1.y + tid];
-                mn = stage[kDecPayloadBytes + kDecPlaneBytes + c1.z + tid];
-            }
-            const uint32_t incl = warp_inclusive_scan((uint32_t)k, lane);
-            const uint32_t woff = S.ctl[s].wbase[warp] + incl - (uint32_t)k;
-            const uint32_t m4 = mn * 0x01010101u;
             uint32_t px[16];
-            if (k > 0) {
-                uint32_t q[16];
-                const uint8_t *pay = stage + pres + 8 * (size_t)woff;
-                if ((pres & 7u) == 0) load_split_any<8>(k, pay, q);     // the usual case: records on 8-byte boundaries
-                else load_split_any<1>(k, pay, q);
-                const uint32_t c1n = 256u - (1u << k), c2n = 65536u - (1u << (2 * k));
-                const uint32_t kmask2 = ((1u << k) - 1u) * 0x00010001u;
-#pragma unroll
-                for (int i = 0; i < 16; i++) px[i] = spread4(q[i], k, c1n, c2n, kmask2) + m4;   // +min (dbde_util.cpp:246)
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; i++) px[i] = m4;                                        // depth 0 (dbde_util.cpp:218-226)
-            }
+            dec_unpack_tile(stage, c1, S.ctl[s].wbase[warp], tid, lane, valid, px);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.empty[s]);       // payload is in registers: free the stage early
@@ -458,6 +490,184 @@ __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecPa
     }
 }
 
+// ------------------------------------------------------------------ staged-store kernel (odd sizes, W <= 2048)
+// Frames whose rows are not 8-byte aligned (W % 8 != 0), or that end in partial tiles, cannot use the
+// direct row stores: a warp's row would be cut into unaligned pieces.  But a full-width partition's
+// pixels are ONE contiguous byte range of the frame -- rows 8*y0 .. of W bytes each, back to back --
+// so the tile warps build that range in shared memory exactly as it lies in global memory (row pitch
+// W, shifted by the range's global address mod 16 so both sides agree on 16-byte boundaries), and a
+// store warp sends the 16-byte-aligned interior out with ONE bulk-TMA store (cp.async.bulk
+// shared -> global, SASS UBLKCP) and the < 16 head and tail bytes with byte stores.  The crop of
+// dbde_unpack_8x8_partial (dbde_util.cpp:281-289) happens on the way into shared memory: lanes of the
+// last tile column write only their valid columns, rows past H are not written at all.
+//   warps 0-7 tile warps, warp 8 producer (loads), warp 9 store warp.
+constexpr int kStgStages = 2;                                    // input stages
+constexpr int kStgThreads = kTilesPerPart + 64;
+constexpr int kStgOutBytes = 64 * kTilesPerPart + 128;           // image of <= 16 KiB + the 16-byte shift, 128-byte multiple
+using StgSmem = DecSmemT<kStgStages>;
+
+__device__ __forceinline__ void tma_store_1d(void *gdst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+// 8 bytes {lo, hi} to shared memory at any byte address, as naturally aligned pieces.  `a` = address & 7 is
+// the same for every lane of a warp (tiles are 8 bytes apart), so the switch is warp-uniform.
+__device__ __forceinline__ void sts_row8(uint8_t *p, uint32_t a, uint32_t lo, uint32_t hi) {
+    switch (a) {
+        case 0: *reinterpret_cast<uint2 *>(p) = make_uint2(lo, hi); break;
+        case 4:
+            *reinterpret_cast<uint32_t *>(p) = lo;
+            *reinterpret_cast<uint32_t *>(p + 4) = hi;
+            break;
+        case 2:
+        case 6:
+            *reinterpret_cast<uint16_t *>(p) = (uint16_t)lo;
+            *reinterpret_cast<uint32_t *>(p + 2) = __funnelshift_r(lo, hi, 16);
+            *reinterpret_cast<uint16_t *>(p + 6) = (uint16_t)(hi >> 16);
+            break;
+        case 1:
+        case 5:
+            p[0] = (uint8_t)lo;
+            *reinterpret_cast<uint16_t *>(p + 1) = (uint16_t)(lo >> 8);
+            *reinterpret_cast<uint32_t *>(p + 3) = __funnelshift_r(lo, hi, 24);
+            p[7] = (uint8_t)(hi >> 24);
+            break;
+        default:      // 3, 7
+            p[0] = (uint8_t)lo;
+            *reinterpret_cast<uint32_t *>(p + 1) = __funnelshift_r(lo, hi, 8);
+            *reinterpret_cast<uint16_t *>(p + 5) = (uint16_t)(hi >> 8);
+            p[7] = (uint8_t)(hi >> 24);
+            break;
+    }
+}
+
+__global__ void __launch_bounds__(kStgThreads, 3) dbde_decode_staged_kernel(const DecParams P) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    StgSmem &S = *reinterpret_cast<StgSmem *>(smem_raw);
+    uint8_t *stages = smem_raw + ((sizeof(StgSmem) + 127) & ~127);
+    uint8_t *outst = stages + (size_t)kStgStages * kDecStageBytes;
+    const PartGeom &g = P.g;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const size_t fbytes = (size_t)g.W * g.H;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStgStages; s++) {
+            mbar_init(&S.full[s], 1);
+            mbar_init(&S.empty[s], kConsumerWarps + 1);        // tile warps + the store warp (reads the control block)
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&S.outfull[s], kConsumerWarps);
+            mbar_init(&S.outempty[s], 1);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == kConsumerWarps) {
+        dec_producer<kStgStages, 0xffffffffu>(P, S, stages, lane);
+    } else if (warp == kConsumerWarps + 1) {
+        // ============================ store warp ============================
+        unsigned oi = 0;                                   // partitions actually stored (skipped frames do not count)
+        for (unsigned it = 0;; it++) {
+            const int s = it % kStgStages;
+            mbar_wait_sleepy(&S.full[s], (it / kStgStages) & 1);
+            const int4 c0 = *reinterpret_cast<const int4 *>(&S.ctl[s].part);      // part, skip, f, nt
+            const uint32_t pixoff = S.ctl[s].pixoff;
+            const int y0 = S.ctl[s].y0;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.empty[s]);
+            if (c0.x < 0) break;
+            if (c0.y) continue;
+            const int os = oi & 1;
+            const int nbands = c0.w / g.w;
+            const int rows = min(8 * nbands, g.H - 8 * y0);
+            const uint32_t n = (uint32_t)rows * (uint32_t)g.W;
+            uint8_t *g0 = P.frames + (size_t)c0.z * fbytes + pixoff;
+            const uint32_t a16 = (uint32_t)(uintptr_t)g0 & 15u;
+            const uint8_t *img = outst + (size_t)os * kStgOutBytes + a16;          // img[i] <-> g0[i]
+            const uint32_t head = min((16u - a16) & 15u, n);                       // bytes before the first 16-byte boundary
+            const uint32_t mid = (n - head) & ~15u;                                // the aligned interior
+            const uint32_t tail = n - head - mid;
+            mbar_wait_sleepy(&S.outfull[os], (oi >> 1) & 1);
+            if (lane == 0 && mid) {
+                tma_store_1d(g0 + head, img + head, mid);
+            }
+            if (lane == 0) tma_store_commit();
+            if (lane < 16) {
+                if ((uint32_t)lane < head) g0[lane] = img[lane];
+            } else {
+                const uint32_t i = head + mid + (uint32_t)(lane - 16);
+                if ((uint32_t)(lane - 16) < tail) g0[i] = img[i];
+            }
+            __syncwarp();
+            // hand the buffer back as soon as the bulk store has READ it (the global writes may still be in
+            // flight); this also keeps shared memory alive until the last store's reads are done
+            if (lane == 0) {
+                tma_store_wait_read<0>();
+                mbar_arrive(&S.outempty[os]);
+            }
+            oi++;
+        }
+    } else {
+        // ============================ tile warps: one lane == one 8x8 tile ============================
+        const int sb = tid / g.w, stx = tid - sb * g.w;
+        const uint32_t toff = (uint32_t)(8 * sb) * (uint32_t)g.W + 8u * (uint32_t)stx;   // my tile inside the image
+        const int ncol = min(8, g.W - 8 * stx);
+        unsigned oi = 0;
+        for (unsigned it = 0;; it++) {
+            const int s = it % kStgStages;
+            mbar_wait(&S.full[s], (it / kStgStages) & 1);
+            const int4 c0 = *reinterpret_cast<const int4 *>(&S.ctl[s].part);      // part, skip, f, nt
+            if (c0.x < 0) break;
+            if (c0.y) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.empty[s]);
+                continue;
+            }
+            const uint4 c1 = *reinterpret_cast<const uint4 *>(&S.ctl[s].pres);    // pres, kres, mres, pixoff
+            const int y0 = S.ctl[s].y0;
+            const uint8_t *stage = stages + (size_t)s * kDecStageBytes;
+            const bool valid = tid < c0.w;
+            uint32_t px[16];
+            dec_unpack_tile(stage, c1, S.ctl[s].wbase[warp], tid, lane, valid, px);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.empty[s]);       // payload is in registers: free the stage early
+
+            const int os = oi & 1;
+            if (oi >= 2) mbar_wait(&S.outempty[os], ((oi >> 1) - 1) & 1);
+            const uint32_t a16 = (uint32_t)((uintptr_t)P.frames + (size_t)c0.z * fbytes + c1.w) & 15u;
+            uint8_t *img = outst + (size_t)os * kStgOutBytes + a16;
+            const int rows_valid = valid ? min(8, g.H - 8 * (y0 + sb)) : 0;
+            uint8_t *rp = img + toff;
+            if (ncol == 8) {
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    if (r < rows_valid) sts_row8(rp, smem_u32(rp) & 7u, px[2 * r], px[2 * r + 1]);
+                    rp += g.W;
+                }
+            } else {
+                // last tile column of an odd-width frame: only the valid columns (a few lanes per partition)
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    if (r < rows_valid) {
+                        const uint64_t x = ((uint64_t)px[2 * r + 1] << 32) | px[2 * r];
+                        for (int c = 0; c < ncol; c++) rp[c] = (uint8_t)(x >> (8 * c));
+                    }
+                    rp += g.W;
+                }
+            }
+            fence_proxy_async();                           // my generic-proxy writes, then the store warp's bulk read
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.outfull[os]);
+            oi++;
+        }
+    }
+}
+
 size_t dec_smem_bytes(const PartGeom &g) {
     (void)g;
     return ((sizeof(DecSmem) + 127) & ~(size_t)127) + (size_t)kDecStages * kDecStageBytes;
@@ -469,20 +679,31 @@ cudaError_t launch_decode_scan(const DecParams &P, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_decode(const DecParams &P, bool fast, int num_sms, cudaStream_t stream) {
-    const size_t smem = dec_smem_bytes(P.g);
-    auto kern = fast ? dbde_decode_kernel<true> : dbde_decode_kernel<false>;
+static size_t stg_smem_bytes() {
+    return ((sizeof(StgSmem) + 127) & ~(size_t)127) + (size_t)kStgStages * kDecStageBytes + 2 * (size_t)kStgOutBytes;
+}
+
+template <typename Kern>
+static cudaError_t launch_persistent(Kern kern, const DecParams &P, int threads, size_t smem, int num_sms, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kDecThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
     unsigned grid = (unsigned)(num_sms * occ);
     if (grid > P.nparts) grid = P.nparts;
     if (grid == 0) return cudaSuccess;
-    kern<<<grid, kDecThreads, smem, stream>>>(P);
+    kern<<<grid, threads, smem, stream>>>(P);
     return cudaGetLastError();
+}
+
+cudaError_t launch_decode(const DecParams &P, bool fast, int num_sms, cudaStream_t stream) {
+    if (fast) return launch_persistent(dbde_decode_kernel<true>, P, kDecThreads, dec_smem_bytes(P.g), num_sms, stream);
+    // odd sizes: full-width partitions (W <= 2048) stage their pixels and store them in bulk; wider
+    // odd frames (band segments are not contiguous in the frame) keep the direct generic stores
+    if (P.g.nseg == 1) return launch_persistent(dbde_decode_staged_kernel, P, kStgThreads, stg_smem_bytes(), num_sms, stream);
+    return launch_persistent(dbde_decode_kernel<false>, P, kDecThreads, dec_smem_bytes(P.g), num_sms, stream);
 }
 
 }  // namespace dbde

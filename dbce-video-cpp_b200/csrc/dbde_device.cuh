@@ -301,6 +301,57 @@ __device__ __forceinline__ void split_fields(const uint32_t (&x)[16], uint32_t (
     }
 }
 
+// ------------------------------------------------------------------ depth-agnostic pack / unpack
+// concat_fields<K> / split_fields<K> are the shortest code for ONE depth, but a warp whose 32 tiles
+// hold many different depths runs one specialisation after the other.  Tile row r is exactly k bytes
+// at byte k*r of the tile's payload (8 pixels x k bits), so a row can also be moved with
+// byte-granular VARIABLE shifts: the same instruction stream for every depth 1..8, no divergence.
+// The tile warps vote per partition and take this path when the warp holds three or more depths.
+
+// unpack: rows of k bytes at pay + k*r -> px[2r], px[2r+1] (before +min).  `pay` may have any byte
+// alignment; reads at most 11 bytes past a row's first byte (the stage has that slack).
+__device__ __forceinline__ void unpack_rows_var(const uint8_t *pay, int k, uint32_t (&px)[16], uint32_t m4) {
+    const uint32_t a0 = smem_u32(pay);
+    const uint32_t fmask = 0xffffffffu >> (32 - 4 * k);
+    const uint32_t c1n = 256u - (1u << k), c2n = 65536u - (1u << (2 * k));
+    const uint32_t kmask2 = ((1u << k) - 1u) * 0x00010001u;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint32_t a = a0 + (uint32_t)(k * r);
+        const uint32_t *wv = reinterpret_cast<const uint32_t *>(pay + k * r - (a & 3u));
+        const uint32_t w0 = wv[0], w1 = wv[1], w2 = wv[2];
+        const uint32_t sh = a << 3;                                   // funnel shifts use the low 5 bits: 8 * (a & 3)
+        const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+        const uint32_t f0 = lo & fmask;
+        const uint32_t f1 = __funnelshift_rc(lo, hi, 4 * k) & fmask;  // clamped: 4k == 32 selects hi
+        px[2 * r] = spread4(f0, k, c1n, c2n, kmask2) + m4;
+        px[2 * r + 1] = spread4(f1, k, c1n, c2n, kmask2) + m4;
+    }
+}
+
+// pack: q[16] = the sixteen 4k-bit fields (squeeze4) -> k U64 words at wp (8-byte aligned shared
+// memory).  A 64-bit accumulator takes one k-byte row per step at byte position (k*r) & 7 and is
+// flushed with a predicated store whenever a word completes.
+__device__ __forceinline__ void pack_rows_var(const uint32_t (&q)[16], int k, uint8_t *wp) {
+    uint64_t acc = 0;
+    uint32_t addr = smem_u32(wp);
+    const uint32_t k4 = 4u * (uint32_t)k;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        // the row as a 64-bit value: q[2r] | q[2r+1] << 4k   (clamped funnel shifts: 4k == 32 is legal)
+        const uint32_t rlo = q[2 * r] | __funnelshift_lc(0u, q[2 * r + 1], k4);
+        const uint32_t rhi = __funnelshift_lc(q[2 * r + 1], 0u, k4);
+        const uint64_t row = ((uint64_t)rhi << 32) | rlo;
+        const uint32_t s = (8u * (uint32_t)(k * r)) & 63u;            // bit position inside the open word: 0, 8, .., 56
+        acc |= row << s;
+        if (s + 8u * (uint32_t)k >= 64u) {                            // the open word is complete (predicated, not a branch)
+            asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(acc) : "memory");
+            addr += 8u;
+            acc = s ? row >> (64u - s) : 0ull;                        // spill-over (s == 0 only at depth 8: none)
+        }
+    }
+}
+
 // unaligned-safe shared loads for the generic (odd width / odd offset) paths
 __device__ __forceinline__ uint32_t lds_u32_unaligned(const uint8_t *p) {
     uint32_t a = smem_u32(p);

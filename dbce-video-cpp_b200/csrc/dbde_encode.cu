@@ -29,6 +29,9 @@
 
 namespace dbde {
 
+#ifndef DBDE_ENC_VAR_MIN_DEPTHS
+#define DBDE_ENC_VAR_MIN_DEPTHS 4
+#endif
 constexpr int kEncRing = 4;        // bookkeeping slots (aggregates, bases): a tile warp is <= 2 partitions ahead of the scan warp
 constexpr int kEncThreads = kTilesPerPart + 64;
 
@@ -344,6 +347,9 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
             const uint32_t off = incl - (uint32_t)k;
             uint8_t *stage_out = outring + ((size_t)(it & 1) * kConsumerWarps + warp) * kEncWarpBytes;
             // ---- stage (4): pack (p - min) into k U64 words, staged linearly in the dead pixel bytes
+            // a warp holding many different depths would run concat_fields<K> once per depth: from
+            // DBDE_VAR_MIN_DEPTHS distinct non-zero depths on, the depth-agnostic row packer is shorter
+            const bool many_depths = __popc(__reduce_or_sync(0xffffffffu, (1u << k) >> 1)) >= DBDE_ENC_VAR_MIN_DEPTHS;
             if (k > 0) {
                 const uint32_t c1 = (1u << k) - 256u, c2 = (1u << (2 * k)) - 65536u;
                 uint32_t q[16];
@@ -351,7 +357,8 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
                 for (int i = 0; i < 16; i++) q[i] = squeeze4(px[i], c1, c2);
                 uint2 *wp = reinterpret_cast<uint2 *>(stage_out + 8 * off);
                 auto store = [&](int n, uint32_t lo, uint32_t hi) { wp[n] = make_uint2(lo, hi); };
-                switch (k) {
+                if (many_depths) pack_rows_var(q, k, stage_out + 8 * off);
+                else switch (k) {
                     case 1: concat_fields<1>(q, store); break;
                     case 2: concat_fields<2>(q, store); break;
                     case 3: concat_fields<3>(q, store); break;
