@@ -514,34 +514,35 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
-// 8 bytes {lo, hi} to shared memory at any byte address, as naturally aligned pieces.  `a` = address & 7 is
-// the same for every lane of a warp (tiles are 8 bytes apart), so the switch is warp-uniform.
-__device__ __forceinline__ void sts_row8(uint8_t *p, uint32_t a, uint32_t lo, uint32_t hi) {
-    switch (a) {
-        case 0: *reinterpret_cast<uint2 *>(p) = make_uint2(lo, hi); break;
-        case 4:
-            *reinterpret_cast<uint32_t *>(p) = lo;
-            *reinterpret_cast<uint32_t *>(p + 4) = hi;
-            break;
-        case 2:
-        case 6:
-            *reinterpret_cast<uint16_t *>(p) = (uint16_t)lo;
-            *reinterpret_cast<uint32_t *>(p + 2) = __funnelshift_r(lo, hi, 16);
-            *reinterpret_cast<uint16_t *>(p + 6) = (uint16_t)(hi >> 16);
-            break;
-        case 1:
-        case 5:
-            p[0] = (uint8_t)lo;
-            *reinterpret_cast<uint16_t *>(p + 1) = (uint16_t)(lo >> 8);
-            *reinterpret_cast<uint32_t *>(p + 3) = __funnelshift_r(lo, hi, 24);
-            p[7] = (uint8_t)(hi >> 24);
-            break;
-        default:      // 3, 7
-            p[0] = (uint8_t)lo;
-            *reinterpret_cast<uint32_t *>(p + 1) = __funnelshift_r(lo, hi, 8);
-            *reinterpret_cast<uint16_t *>(p + 5) = (uint16_t)(hi >> 8);
-            p[7] = (uint8_t)(hi >> 24);
-            break;
+// 8 bytes {lo, hi} to shared memory at any byte address, as naturally aligned pieces.  `a` = the
+// address's low bits, passed separately because the caller derives it from block-uniform values
+// (partition id -> frame, band -> global address of the row): the branches below are then uniform
+// branches, not divergent ones.  Three shapes: a % 4 == 0 -> 8 or 4+4; a % 4 == 2 -> 2+4+2;
+// odd -> 1+2+2+2+1 (the same code serves a % 4 == 1 and 3: every 2-byte piece lands on an even address).
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+    asm volatile("{ .reg .b16 t; cvt.u16.u32 t, %1; st.shared.u16 [%0], t; }" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_v2u32(uint32_t addr, uint32_t lo, uint32_t hi) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(lo), "r"(hi) : "memory");
+}
+__device__ __forceinline__ void sts_row8(uint32_t addr, uint32_t a, uint32_t lo, uint32_t hi) {
+    if (a & 1u) {
+        sts_u8(addr, lo);
+        sts_u16(addr + 1, lo >> 8);
+        sts_u16(addr + 3, __funnelshift_r(lo, hi, 24));
+        sts_u16(addr + 5, hi >> 8);
+        sts_u8(addr + 7, hi >> 24);
+    } else if (a & 2u) {
+        sts_u16(addr, lo);
+        sts_u32(addr + 2, __funnelshift_r(lo, hi, 16));
+        sts_u16(addr + 6, hi >> 16);
+    } else if (a & 4u) {
+        sts_u32(addr, lo);
+        sts_u32(addr + 4, hi);
+    } else {
+        sts_v2u32(addr, lo, hi);
     }
 }
 
@@ -639,23 +640,31 @@ __global__ void __launch_bounds__(kStgThreads, 3) dbde_decode_staged_kernel(cons
 
             const int os = oi & 1;
             if (oi >= 2) mbar_wait(&S.outempty[os], ((oi >> 1) - 1) & 1);
-            const uint32_t a16 = (uint32_t)((uintptr_t)P.frames + (size_t)c0.z * fbytes + c1.w) & 15u;
-            uint8_t *img = outst + (size_t)os * kStgOutBytes + a16;
+            // The image's global address, recomputed from the partition id: the producer walks the
+            // partitions in the static order blockIdx.x + it * gridDim.x, so frame and band are
+            // block-uniform here and the row alignments below are uniform values.
+            const unsigned up = blockIdx.x + it * gridDim.x;
+            const unsigned uf = up / (unsigned)g.ppf, uq = up - uf * (unsigned)g.ppf;
+            const uint32_t ag = (uint32_t)((uintptr_t)P.frames + (size_t)uf * fbytes + (size_t)(8u * uq * (unsigned)g.G) * (size_t)g.W);
+            const uint32_t img = smem_u32(outst) + (uint32_t)os * kStgOutBytes + (ag & 15u);
             const int rows_valid = valid ? min(8, g.H - 8 * (y0 + sb)) : 0;
-            uint8_t *rp = img + toff;
-            if (ncol == 8) {
+            uint32_t rp = img + toff;
+            if (rows_valid == 8 && ncol == 8) {
+                uint32_t a = ag;                            // image row alignment (tiles are 8 bytes apart: same for every lane)
 #pragma unroll
                 for (int r = 0; r < 8; r++) {
-                    if (r < rows_valid) sts_row8(rp, smem_u32(rp) & 7u, px[2 * r], px[2 * r + 1]);
+                    sts_row8(rp, a, px[2 * r], px[2 * r + 1]);
                     rp += g.W;
+                    a += g.W;
                 }
             } else {
-                // last tile column of an odd-width frame: only the valid columns (a few lanes per partition)
+                // last tile column of an odd-width frame / last band of an odd-height one: only the
+                // valid columns and rows (dbde_util.cpp:281-289); a few lanes per partition
 #pragma unroll
                 for (int r = 0; r < 8; r++) {
                     if (r < rows_valid) {
                         const uint64_t x = ((uint64_t)px[2 * r + 1] << 32) | px[2 * r];
-                        for (int c = 0; c < ncol; c++) rp[c] = (uint8_t)(x >> (8 * c));
+                        for (int c = 0; c < ncol; c++) sts_u8(rp + c, (uint32_t)(x >> (8 * c)));
                     }
                     rp += g.W;
                 }

@@ -84,7 +84,10 @@ constexpr int kWidePitch = 8 * kTilesPerPart;
 // WIDE : FAST and w % 256 == 0 (2048-, 4096-pixel-wide frames): every partition is one full 256-tile
 //        band segment, so the smem pitch is the constant 2048 (immediate-offset row loads) and no
 //        lane is ever idle.
-template <bool FAST, bool WIDE>
+// CONTIG: odd sizes whose partitions span the full width (W <= 2048): the partition's pixels are one
+//        contiguous byte range of the frame, staged with ONE bulk copy of its 16-byte hull at row
+//        pitch W; a lane's row is then `first row + r * W`, read as aligned words + funnel shift.
+template <bool FAST, bool WIDE, bool CONTIG>
 __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     EncSmem &S = *reinterpret_cast<EncSmem *>(smem_raw);
@@ -142,6 +145,19 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
                     *reinterpret_cast<int4 *>(&S.ctl[s].q) = make_int4(pi.q, pi.y0, pi.tx0, 0);
                     mbar_arrive_expect_tx(&S.full[s], bytes);
                     tma_load_1d(stage, fptr + (size_t)(8 * pi.y0) * g.W, bytes, &S.full[s]);
+                }
+                continue;
+            }
+            if (CONTIG) {
+                if (lane == 0) {
+                    const uint8_t *g0 = fptr + (size_t)(8 * pi.y0) * g.W;
+                    const uint32_t n = (uint32_t)min(nrows, g.H - 8 * pi.y0) * (uint32_t)g.W;
+                    const uintptr_t a0 = (uintptr_t)g0 & ~(uintptr_t)15;
+                    const uintptr_t a1 = ((uintptr_t)g0 + n + 15) & ~(uintptr_t)15;
+                    *reinterpret_cast<int4 *>(&S.ctl[s].part) = make_int4((int)p, pi.f, pi.tfirst, pi.nt);
+                    *reinterpret_cast<int4 *>(&S.ctl[s].q) = make_int4(pi.q, pi.y0, pi.tx0, (int)((uintptr_t)g0 - a0));
+                    mbar_arrive_expect_tx(&S.full[s], (uint32_t)(a1 - a0));
+                    tma_load_1d(stage, (const void *)a0, (uint32_t)(a1 - a0), &S.full[s]);
                 }
                 continue;
             }
@@ -305,6 +321,42 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
                     px[2 * r] = v.x;
                     px[2 * r + 1] = v.y;
                 }
+            } else if (CONTIG) {
+                const int4 c1 = *reinterpret_cast<const int4 *>(&S.ctl[s].q);      // q, y0, tx0, first pixel's offset in the hull
+                const int rows_valid = min(8, g.H - 8 * (c1.y + sb));
+                const int ncol = min(8, g.W - 8 * stx);
+                uint32_t addr = smem_u32(stage) + (uint32_t)c1.w + (valid ? toff : 0u);      // idle lanes read (and discard) tile 0
+                auto load8 = [&](uint32_t a) {
+                    uint32_t w0, w1, w2;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(a & ~3u));
+                    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(a & ~3u));
+                    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(a & ~3u));
+                    return make_uint2(__funnelshift_r(w0, w1, a << 3), __funnelshift_r(w1, w2, a << 3));
+                };
+                if (!valid || (rows_valid == 8 && ncol == 8)) {
+#pragma unroll
+                    for (int r = 0; r < 8; r++) {
+                        const uint2 v = load8(addr);
+                        addr += (uint32_t)g.W;
+                        px[2 * r] = v.x;
+                        px[2 * r + 1] = v.y;
+                    }
+                } else {
+                    // clamp-to-edge padding (dbde_util.cpp:105-135), edge tiles only
+#pragma unroll
+                    for (int r = 0; r < 8; r++) {
+                        uint2 v = load8(addr + (uint32_t)(min(r, rows_valid - 1) * g.W));
+                        if (ncol < 8) {
+                            uint64_t x = ((uint64_t)v.y << 32) | v.x;
+                            const uint64_t last = (x >> (8 * (ncol - 1))) & 0xffull;
+                            const uint64_t keep = (1ull << (8 * ncol)) - 1ull;
+                            x = (x & keep) | ((last * 0x0101010101010101ull) & ~keep);
+                            v = make_uint2((uint32_t)x, (uint32_t)(x >> 32));
+                        }
+                        px[2 * r] = v.x;
+                        px[2 * r + 1] = v.y;
+                    }
+                }
             } else {
                 // clamp-to-edge padding (dbde_util.cpp:105-135): rows past H repeat the last valid
                 // row, columns past W repeat the last valid pixel of the row
@@ -417,10 +469,15 @@ size_t enc_smem_bytes(const PartGeom &g) {
     return ((sizeof(EncSmem) + 127) & ~(size_t)127) + (size_t)kEncStages * g.stage_bytes + 2 * (size_t)kConsumerWarps * kEncWarpBytes;
 }
 
-cudaError_t launch_encode(const EncParams &P, bool fast, int num_sms, cudaStream_t stream) {
+cudaError_t launch_encode(const EncParams &Pin, bool fast, int num_sms, cudaStream_t stream) {
+    EncParams P = Pin;
     const size_t smem = enc_smem_bytes(P.g);
     const bool wide = fast && (P.g.w % kTilesPerPart == 0) && P.g.pitch == kWidePitch;
-    auto kern = wide ? dbde_encode_kernel<true, true> : (fast ? dbde_encode_kernel<true, false> : dbde_encode_kernel<false, false>);
+    const bool contig = !fast && P.g.nseg == 1;
+    if (contig) P.g.pitch = P.g.W;        // the stage holds the partition's pixels exactly as they lie in the frame
+    auto kern = wide ? dbde_encode_kernel<true, true, false>
+                     : (fast ? dbde_encode_kernel<true, false, false>
+                             : (contig ? dbde_encode_kernel<false, false, true> : dbde_encode_kernel<false, false, false>));
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 0;
