@@ -501,6 +501,9 @@ __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecPa
 // dbde_unpack_8x8_partial (dbde_util.cpp:281-289) happens on the way into shared memory: lanes of the
 // last tile column write only their valid columns, rows past H are not written at all.
 //   warps 0-7 tile warps, warp 8 producer (loads), warp 9 store warp.
+// Measured on mix/micro/noise/low 1001x1003: 3 input stages (2 CTAs/SM) -11 %; spinning instead of sleeping in
+// the store warp: no change; without the bulk store: -3 % time; without the shared-memory row stores:
+// -30 % -- the unaligned row stores (narrow pieces, 2-way bank conflicts), not the TMA traffic, are the cost.
 constexpr int kStgStages = 2;                                    // input stages
 constexpr int kStgThreads = kTilesPerPart + 64;
 constexpr int kStgOutBytes = 64 * kTilesPerPart + 128;           // image of <= 16 KiB + the 16-byte shift, 128-byte multiple
@@ -594,9 +597,7 @@ __global__ void __launch_bounds__(kStgThreads, 3) dbde_decode_staged_kernel(cons
             const uint32_t mid = (n - head) & ~15u;                                // the aligned interior
             const uint32_t tail = n - head - mid;
             mbar_wait_sleepy(&S.outfull[os], (oi >> 1) & 1);
-            if (lane == 0 && mid) {
-                tma_store_1d(g0 + head, img + head, mid);
-            }
+            if (lane == 0 && mid) tma_store_1d(g0 + head, img + head, mid);
             if (lane == 0) tma_store_commit();
             if (lane < 16) {
                 if ((uint32_t)lane < head) g0[lane] = img[lane];

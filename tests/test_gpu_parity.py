@@ -132,6 +132,45 @@ def test_sizes_and_edges(codec, W, H):
     roundtrip_check(codec, frames, first_index=1000)
 
 
+@pytest.mark.parametrize("W,H", [(1002, 19), (1004, 21), (1006, 17), (1003, 8), (2047, 17), (2041, 33), (2044, 9),
+                                 (5, 1000), (33, 515), (15, 64), (250, 250), (1999, 41)])
+def test_odd_sizes_full_width_partitions(codec, W, H):
+    """W <= 2048 with W % 16 != 0 or H % 8 != 0: the contiguous-hull encoder staging and the staged-store
+    decoder (every row alignment class: W % 8 = 1..7, 2, 4, 6; one to eight bands per partition)"""
+    rng = np.random.default_rng(W * 7919 + H)
+    frames = np.stack([rand_frame(rng, W, H, ["classes", "noise", "flat", "classes"][i % 4]) for i in range(4)])
+    roundtrip_check(codec, frames, first_index=7)
+    roundtrip_check(codec, synth.gen_frames("mix", 3, W, H, f0=5))
+
+
+def test_rejected_frames_between_good_ones_odd_size(codec):
+    """the staged-store decoder skips rejected frames without losing step with its store warp
+    (dbde_util.cpp:296-303: image untouched), odd size, several partitions per frame"""
+    W, H, N = 1001, 43, 9
+    wh = ((W + 7) // 8) * ((H + 7) // 8)
+    fr = synth.gen_frames("mix", N, W, H)
+    stream, sizes = ORA.pack_frames(fr, 0)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    bad = stream.copy()
+    for i in (0, 3, 4, 8):
+        bad[int(offs[i]) + 28 + 2 * wh] ^= 1       # n64 != sum(depth)
+    dec, status, _ = codec.decode_host(bad, offs[:N], W, H, fill=0xCD)
+    for i in range(N):
+        if i in (0, 3, 4, 8):
+            assert status[i] == pkg.ST_BAD_WORD_COUNT and (dec[i] == 0xCD).all(), i
+        else:
+            assert status[i] == 0 and (dec[i] == fr[i]).all(), i
+
+
+@pytest.mark.parametrize("W,H", [(512, 64), (2048, 24), (4096, 16), (264, 40)])
+def test_many_depths_per_warp_aligned(codec, W, H):
+    """all nine depths inside every warp on the aligned kernels: the depth-agnostic row packer /
+    unpacker (taken when a warp holds several depths) against the per-depth specialisations' oracle"""
+    roundtrip_check(codec, synth.gen_frames("mix", 5, W, H, f0=3))
+    rng = np.random.default_rng(W + H)
+    roundtrip_check(codec, np.stack([rand_frame(rng, W, H, "classes") for _ in range(3)]))
+
+
 def test_every_depth_class_uniform(codec):
     """a whole frame at each depth 0..8 (uniform-depth warps hit the worst staging strides)"""
     rng = np.random.default_rng(11)
