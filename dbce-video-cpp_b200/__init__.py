@@ -32,6 +32,7 @@ C_SYMBOLS = [
     "dbde_b200_encode_device", "dbde_b200_decode_device", "dbde_b200_encode_host", "dbde_b200_decode_host",
     "dbde_b200_encode_host_sharded", "dbde_b200_decode_host_sharded",
     "dbde_b200_index_stream", "dbde_b200_set_chunk_frames", "dbde_b200_kernel_launches",
+    "dbde_b200_set_format_variants", "dbde_b200_get_format_variants", "dbde_b200_set_invert_endian",
     "dbde_b200_writer_open", "dbde_b200_writer_append", "dbde_b200_writer_close",
     "dbde_b200_reader_open", "dbde_b200_reader_next", "dbde_b200_reader_close", "dbde_b200_file_last_error",
 ]
@@ -99,6 +100,11 @@ def load():
     lib.dbde_b200_index_stream.restype = C.c_long
     lib.dbde_b200_index_stream.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_long]
     lib.dbde_b200_set_chunk_frames.argtypes = [C.c_void_p, C.c_int]
+    lib.dbde_b200_set_format_variants.restype = None
+    lib.dbde_b200_set_format_variants.argtypes = [C.c_int, C.c_int]
+    lib.dbde_b200_get_format_variants.restype = None
+    lib.dbde_b200_get_format_variants.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.dbde_b200_set_invert_endian.argtypes = [C.c_void_p, C.c_int]
     lib.dbde_b200_kernel_launches.restype = C.c_uint64
     lib.dbde_b200_kernel_launches.argtypes = [C.c_void_p]
     lib.dbde_b200_writer_open.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_uint64, C.POINTER(C.c_void_p)]
@@ -191,6 +197,10 @@ class Codec:
 
     def set_chunk_frames(self, n):
         self._ck(self.lib.dbde_b200_set_chunk_frames(self.h, n), "set_chunk_frames")
+
+    def set_invert_endian(self, on):
+        """the reference's DBDE_INVERT_ENDIAN build variant for this context (dbde_util.cpp:15-19)"""
+        self._ck(self.lib.dbde_b200_set_invert_endian(self.h, int(bool(on))), "set_invert_endian")
 
     # ---- device-resident hot path (raw device pointers, asynchronous on `stream`)
     def encode_device(self, frames_ptr, W, H, first_index, n, out_ptr, out_cap, offs_ptr, sizes_ptr, stream=0,
@@ -339,6 +349,18 @@ class _VideoHeader(C.Structure):
 class _Walker(C.Structure):
     _fields_ = [("fptr", C.c_void_p), ("frames", C.c_int32), ("i", C.c_size_t), ("n", C.c_size_t), ("N", C.c_size_t),
                 ("width", C.c_int32), ("height", C.c_int32), ("buffer", C.c_void_p)]
+
+
+def set_format_variants(invert_endian, hz_as_integer):
+    """process-wide: the reference's DBDE_INVERT_ENDIAN / DBDE_HZ_AS_INTEGER build variants (the C++
+    drop-in functions follow it on every call; contexts created afterwards start with it)"""
+    load().dbde_b200_set_format_variants(int(bool(invert_endian)), int(bool(hz_as_integer)))
+
+
+def get_format_variants():
+    a, b = C.c_int(0), C.c_int(0)
+    load().dbde_b200_get_format_variants(C.byref(a), C.byref(b))
+    return bool(a.value), bool(b.value)
 
 
 class DropIn:

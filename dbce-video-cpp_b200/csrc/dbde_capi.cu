@@ -59,6 +59,7 @@ struct dbde_b200_ctx {
     HostSlot slots[kMaxHostSlots];
     int nslots = kDefaultHostSlots;   // staging slots in flight (DBDE_B200_SLOTS)
     int chunk_frames = 0;             // frames per chunk, 0 = auto (DBDE_B200_CHUNK_FRAMES)
+    int invert_endian = 0;            // DBDE_INVERT_ENDIAN variant; initialised from the process-wide setting
     uint64_t launches = 0;
 };
 
@@ -104,6 +105,28 @@ static size_t payload_align_delta(int W, int H) {
     return (16 - (32 + 2 * wh) % 16) % 16;
 }
 
+// ------------------------------------------------------------------ format variants
+// The reference's two compile-time variants.  Building this library with the same
+// macros makes them the defaults; dbde_b200_set_format_variants() switches them at run time.
+#ifdef DBDE_INVERT_ENDIAN
+static int g_invert_endian = 1;
+#else
+static int g_invert_endian = 0;
+#endif
+#ifdef DBDE_HZ_AS_INTEGER
+static int g_hz_as_integer = 1;
+#else
+static int g_hz_as_integer = 0;
+#endif
+extern "C" void dbde_b200_set_format_variants(int invert_endian, int hz_as_integer) {
+    g_invert_endian = invert_endian ? 1 : 0;
+    g_hz_as_integer = hz_as_integer ? 1 : 0;
+}
+extern "C" void dbde_b200_get_format_variants(int *invert_endian, int *hz_as_integer) {
+    if (invert_endian) *invert_endian = g_invert_endian;
+    if (hz_as_integer) *hz_as_integer = g_hz_as_integer;
+}
+
 // ------------------------------------------------------------------ lifetime
 extern "C" int dbde_b200_device_count(void) {
     int n = 0;
@@ -127,6 +150,7 @@ extern "C" int dbde_b200_create(int device, dbde_b200_ctx **out) {
     dbde_b200_ctx *c = new dbde_b200_ctx();
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
+    c->invert_endian = g_invert_endian;
     if (const char *e = getenv("DBDE_B200_SLOTS")) {
         const int n = atoi(e);
         if (n >= 2 && n <= kMaxHostSlots) c->nslots = n;
@@ -166,6 +190,12 @@ extern "C" void dbde_b200_destroy(dbde_b200_ctx *c) {
 
 extern "C" const char *dbde_b200_last_error(void) { return g_err.c_str(); }
 extern "C" uint64_t dbde_b200_kernel_launches(const dbde_b200_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int dbde_b200_set_invert_endian(dbde_b200_ctx *c, int on) {
+    if (!c) return fail(DBDE_B200_E_INVALID, "set_invert_endian: bad argument");
+    c->invert_endian = on ? 1 : 0;
+    return 0;
+}
 
 extern "C" int dbde_b200_set_chunk_frames(dbde_b200_ctx *c, int frames) {
     if (!c || frames < 0) return fail(DBDE_B200_E_INVALID, "set_chunk_frames: bad argument");
@@ -265,6 +295,7 @@ extern "C" int dbde_b200_encode_device(dbde_b200_ctx *c, const uint8_t *frames_d
     P.first_index = first_index;
     P.nframes = nframes;
     P.nparts = (unsigned)nparts;
+    P.flags = c->invert_endian ? kFlagInvertRows : 0u;
     CK(launch_encode(P, fast, c->num_sms, st));
     c->launches += 1;
     return 0;
@@ -297,6 +328,7 @@ extern "C" int dbde_b200_decode_device(dbde_b200_ctx *c, const uint8_t *stream_d
     P.wprefix = (uint32_t *)c->dec_scratch;
     P.nframes = nframes;
     P.nparts = (unsigned)nparts;
+    P.flags = c->invert_endian ? kFlagInvertRows : 0u;
     CK(launch_decode_scan(P, st));
     CK(launch_decode(P, fast, c->num_sms, st));
     c->launches += 2;

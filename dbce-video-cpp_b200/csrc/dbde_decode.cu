@@ -293,7 +293,7 @@ __device__ __forceinline__ void store_row_generic(uint8_t *rp, uint64_t x, int n
 #define DBDE_VAR_MIN_DEPTHS 3
 #endif
 __device__ __forceinline__ void dec_unpack_tile(const uint8_t *stage, const uint4 &c1, uint32_t wbase, int tid, int lane,
-                                                bool valid, uint32_t (&px)[16]) {
+                                                bool valid, bool invert, uint32_t (&px)[16]) {
     const uint32_t pres = c1.x;
     int k = 0;
     uint32_t mn = 0;
@@ -327,6 +327,7 @@ __device__ __forceinline__ void dec_unpack_tile(const uint8_t *stage, const uint
 #pragma unroll
         for (int i = 0; i < 16; i++) px[i] = m4;                                        // depth 0 (dbde_util.cpp:218-226)
     }
+    if (invert) reverse_rows(px);                                                       // ENDIAN() at dbde_util.cpp:246-270
 }
 
 // ------------------------------------------------------------------ producer warp (both unpack kernels)
@@ -457,7 +458,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecPa
             const uint8_t *stage = stages + (size_t)s * kDecStageBytes;
             const bool valid = tid < c0.w;
             uint32_t px[16];
-            dec_unpack_tile(stage, c1, S.ctl[s].wbase[warp], tid, lane, valid, px);
+            dec_unpack_tile(stage, c1, S.ctl[s].wbase[warp], tid, lane, valid, (P.flags & kFlagInvertRows) != 0, px);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.empty[s]);       // payload is in registers: free the stage early
@@ -635,7 +636,7 @@ __global__ void __launch_bounds__(kStgThreads, 3) dbde_decode_staged_kernel(cons
             const uint8_t *stage = stages + (size_t)s * kDecStageBytes;
             const bool valid = tid < c0.w;
             uint32_t px[16];
-            dec_unpack_tile(stage, c1, S.ctl[s].wbase[warp], tid, lane, valid, px);
+            dec_unpack_tile(stage, c1, S.ctl[s].wbase[warp], tid, lane, valid, (P.flags & kFlagInvertRows) != 0, px);
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.empty[s]);       // payload is in registers: free the stage early
 

@@ -226,6 +226,16 @@ __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, int lane) {
 // ------------------------------------------------------------------ per-tile arithmetic (one lane == one 8x8 tile)
 // px[2r], px[2r+1] = the 8 pixels of tile row r, little-endian.
 
+// DBDE_INVERT_ENDIAN variant: reverse the 8 bytes of every tile row (dbde_util.cpp:15-19)
+__device__ __forceinline__ void reverse_rows(uint32_t (&px)[16]) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint32_t lo = __byte_perm(px[2 * r + 1], 0u, 0x0123), hi = __byte_perm(px[2 * r], 0u, 0x0123);
+        px[2 * r] = lo;
+        px[2 * r + 1] = hi;
+    }
+}
+
 // exact minimum of the 64 bytes: u16x2 min over {w, w<<8} puts every byte in a high-byte slot
 // (VIMNMX3.U16x2; the byte-wise __vminu4 is a 7-instruction emulation on sm_100a).
 __device__ __forceinline__ uint32_t tile_min(const uint32_t (&px)[16]) {

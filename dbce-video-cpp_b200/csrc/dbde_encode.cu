@@ -381,6 +381,7 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
                     px[2 * r + 1] = v.y;
                 }
             }
+            if (P.flags & kFlagInvertRows) reverse_rows(px);      // after the clamp padding, as ENDIAN() at dbde_util.cpp:24-27
             // the pixels are in registers: hand the stage back to the producer right away
             fence_proxy_async();
             __syncwarp();

@@ -38,7 +38,16 @@ dbde_b200_ctx *ctx() {
             abort();
         }
     }
+    int inv = 0;
+    dbde_b200_get_format_variants(&inv, nullptr);       // follow the process-wide DBDE_INVERT_ENDIAN setting
+    dbde_b200_set_invert_endian(t.ctx, inv);
     return t.ctx;
+}
+
+bool hz_as_integer() {
+    int hz = 0;
+    dbde_b200_get_format_variants(nullptr, &hz);
+    return hz != 0;
 }
 
 void die(const char *what, int rc) {
@@ -62,12 +71,13 @@ size_t dbde_pack_frame_header(frame_header fh, uint8_t *target) {
     memcpy(target + 12, &e, 8);
     return 20;
 }
-// reference dbde_util.cpp:198-209 (default build: frame_hz is a double)
+// reference dbde_util.cpp:198-209 (frame_hz is a double; a rounded U64 under DBDE_HZ_AS_INTEGER, :203-204)
 size_t dbde_pack_video_header(video_header vh, uint8_t *target) {
     put32(target, vh.u64s);
     put64(target + 4, vh.height);
     put64(target + 12, vh.width);
-    memcpy(target + 20, &vh.frame_hz, 8);
+    if (hz_as_integer()) put64(target + 20, (uint64_t)(long long)(vh.frame_hz + 0.5));
+    else memcpy(target + 20, &vh.frame_hz, 8);
     return 28;
 }
 // reference dbde_util.cpp:330-337
@@ -90,7 +100,8 @@ video_header dbde_unpack_video_header(uint8_t **packed) {
     vh.u64s = get32(p);
     vh.height = get64(p + 4);
     vh.width = get64(p + 12);
-    memcpy(&vh.frame_hz, p + 20, 8);
+    if (hz_as_integer()) vh.frame_hz = (double)get64(p + 20);      // :352-353
+    else memcpy(&vh.frame_hz, p + 20, 8);
     *packed += 28;
     if (vh.u64s != 3) vh.u64s = (uint32_t)-1;
     return vh;

@@ -16,6 +16,7 @@ struct EncParams {
     uint64_t first_index;
     int nframes;
     unsigned nparts;
+    uint32_t flags;             // kFlagInvertRows
 };
 
 struct DecParams {
@@ -29,7 +30,12 @@ struct DecParams {
     uint32_t *wprefix;          // nframes * (ppf*8 + 1) exclusive word prefixes per partition-warp
     int nframes;
     unsigned nparts;
+    uint32_t flags;             // kFlagInvertRows
 };
+
+// The reference's DBDE_INVERT_ENDIAN build variant (dbde_util.cpp:15-19,24-27,246-270): every 8-pixel tile
+// row is byte-reversed before packing and after unpacking.  A launch-uniform flag here.
+enum : uint32_t { kFlagInvertRows = 1 };
 
 // status bits reported by the decoder (0 = frame decoded)
 enum : uint32_t {

@@ -162,6 +162,17 @@ DBDE_B200_API long dbde_b200_reader_next(dbde_b200_reader *r, uint8_t *frames_ho
 DBDE_B200_API int dbde_b200_reader_close(dbde_b200_reader *r);
 DBDE_B200_API const char *dbde_b200_file_last_error(void);
 
+/* ---- the reference's compile-time format variants --------------------------- */
+/* DBDE_INVERT_ENDIAN (dbde_util.cpp:15-19,24-27,246-270): every 8-pixel tile row is byte-reversed
+ * before packing and after unpacking.  DBDE_HZ_AS_INTEGER (dbde_util.cpp:203-204,352-353): the video
+ * header carries frame_hz as a rounded U64 instead of a double.  Compiling this library with the
+ * same macros makes them its defaults (as in the reference); these calls switch them at run time.
+ * set_format_variants is process-wide: it sets the default of contexts created afterwards, and the
+ * C++ drop-in functions (dbde_util.h) follow it on every call.  set_invert_endian changes one context. */
+DBDE_B200_API void dbde_b200_set_format_variants(int invert_endian, int hz_as_integer);
+DBDE_B200_API void dbde_b200_get_format_variants(int *invert_endian, int *hz_as_integer);
+DBDE_B200_API int dbde_b200_set_invert_endian(dbde_b200_ctx *ctx, int on);
+
 /* Tuning knob for the host path: frames per staged chunk (default: ~64 MiB of pixels). */
 DBDE_B200_API int dbde_b200_set_chunk_frames(dbde_b200_ctx *ctx, int frames);
 

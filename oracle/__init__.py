@@ -162,9 +162,33 @@ port = _Codec(_port_lib, "oracle_")
 _ref_lib = _load(os.path.join(HERE, "_ref", "libdbde_ref.so"))
 ref = _Codec(_ref_lib, "ref_") if _ref_lib is not None else None
 
+# The reference built with -DDBDE_INVERT_ENDIAN -DDBDE_HZ_AS_INTEGER (its two compile-time format
+# variants), and a second instance of the port switched to the same variants.
+_refv_lib = _load(os.path.join(HERE, "_ref", "libdbde_ref_variants.so"))
+ref_variants = _Codec(_refv_lib, "ref_") if _refv_lib is not None else None
+
+
+def port_variants():
+    """A private copy of the port with both variants on (the flag is a global of the library, so the
+    copy is loaded from its own file to leave `port` untouched)."""
+    import shutil
+    import tempfile
+    d = tempfile.mkdtemp(prefix="dbde_oracle_")
+    path = os.path.join(d, "liboracle_variants.so")
+    shutil.copy(os.path.join(HERE, "liboracle.so"), path)
+    lib = C.CDLL(path)
+    lib.oracle_set_variants.argtypes = [C.c_int, C.c_int]
+    lib.oracle_set_variants(1, 1)
+    return _Codec(lib, "oracle_")
+
+
 def best():
     """The strongest checker available: the compiled reference, else the port."""
     return ref if ref is not None else port
+
+
+def best_variants():
+    return ref_variants if ref_variants is not None else port_variants()
 
 
 if _ref_lib is not None:

@@ -24,6 +24,18 @@
 
 #define ORACLE_API __attribute__((visibility("default")))
 
+/* The reference's two compile-time format variants, selectable at run time here so one
+ * checker serves both builds:
+ *   DBDE_INVERT_ENDIAN (dbde_util.cpp:15-19,24-27,246-270): every 8-pixel tile row is byte-reversed
+ *     before packing and after unpacking (pixel column c travels as column 7-c);
+ *   DBDE_HZ_AS_INTEGER (dbde_util.cpp:203-204,352-353): the video header's frame_hz travels as a
+ *     rounded U64 instead of an IEEE-754 double. */
+static int g_invert_endian = 0, g_hz_as_integer = 0;
+ORACLE_API void oracle_set_variants(int invert_endian, int hz_as_integer) {
+    g_invert_endian = invert_endian;
+    g_hz_as_integer = hz_as_integer;
+}
+
 static void put_le(uint8_t *p, uint64_t v, int nbytes) {
     for (int i = 0; i < nbytes; i++) p[i] = (uint8_t)(v >> (8 * i));
 }
@@ -55,7 +67,8 @@ ORACLE_API uint32_t oracle_pack_8x8(const uint8_t *image, int stride, uint8_t *t
     if (k == 0) return lo;
     memset(target, 0, (size_t)(8 * k));
     for (int i = 0; i < 64; i++) {
-        unsigned q = (unsigned)(uint8_t)(image[(i >> 3) * stride + (i & 7)] - lo);  /* :51-55 */
+        int c = g_invert_endian ? 7 - (i & 7) : (i & 7);                            /* ENDIAN(), :15-19,24-27 */
+        unsigned q = (unsigned)(uint8_t)(image[(i >> 3) * stride + c] - lo);        /* :51-55 */
         int bit = k * i;                            /* field i occupies bits [k*i, k*i+k) */
         for (int b = 0; b < k; b++, bit++)
             if ((q >> b) & 1u) target[bit >> 3] |= (uint8_t)(1u << (bit & 7));
@@ -120,11 +133,12 @@ ORACLE_API size_t oracle_pack_frame(uint64_t index, const uint8_t *image, int W,
 }
 
 /* 28-byte video header: I32 u64s | U64 height | U64 width | F64 frame_hz.
- * dbde_util.cpp:198-209 (default build, no DBDE_HZ_AS_INTEGER). */
+ * dbde_util.cpp:198-209 (frame_hz as a rounded U64 under the DBDE_HZ_AS_INTEGER variant). */
 ORACLE_API size_t oracle_pack_video_header(uint32_t u64s, uint64_t height, uint64_t width, double frame_hz,
                                            uint8_t *target) {
     uint64_t hz;
     memcpy(&hz, &frame_hz, 8);
+    if (g_hz_as_integer) hz = (uint64_t)(long long)(frame_hz + 0.5);            /* :203-204 */
     put_le(target, u64s, 4);
     put_le(target + 4, height, 8);
     put_le(target + 12, width, 8);
@@ -143,7 +157,8 @@ ORACLE_API void oracle_unpack_8x8(uint8_t depth, uint8_t minval, const uint8_t *
             int bit = depth * i;
             for (int b = 0; b < depth; b++, bit++) q |= ((packed[bit >> 3] >> (bit & 7)) & 1u) << b;
         }
-        image[(size_t)(i >> 3) * stride + (i & 7)] = (uint8_t)(q + minval);   /* wrapping add, :246 */
+        int c = g_invert_endian ? 7 - (i & 7) : (i & 7);                      /* ENDIAN(), :246-270 */
+        image[(size_t)(i >> 3) * stride + c] = (uint8_t)(q + minval);         /* wrapping add, :246 */
     }
 }
 
@@ -211,7 +226,8 @@ ORACLE_API size_t oracle_unpack_frame(const uint8_t *packed, int W, int H, uint8
 ORACLE_API size_t oracle_unpack_video_header(const uint8_t *packed, uint64_t out_u[3], double *frame_hz) {
     uint32_t u = (uint32_t)get_le(packed, 4);
     uint64_t hz = get_le(packed + 20, 8);
-    memcpy(frame_hz, &hz, 8);
+    if (g_hz_as_integer) *frame_hz = (double)hz;                                /* :352-353 */
+    else memcpy(frame_hz, &hz, 8);
     out_u[0] = (u != 3) ? 0xFFFFFFFFu : u;
     out_u[1] = get_le(packed + 4, 8);
     out_u[2] = get_le(packed + 12, 8);

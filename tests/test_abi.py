@@ -80,3 +80,21 @@ def test_product_never_imports_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert "import oracle" not in src and "oracle/" not in src.replace("never touches oracle/", ""), fn
+
+
+def test_video_header_hz_as_integer_variant_is_host_only(lib):
+    """DBDE_HZ_AS_INTEGER (dbde_util.cpp:203-204,352-353) through the C++ drop-in symbols: pure host
+    marshalling, so it runs without a GPU.  Checked against the oracle's variant."""
+    import numpy as np
+    import oracle
+    d = pkg.DropIn()
+    try:
+        pkg.set_format_variants(False, True)
+        assert pkg.get_format_variants() == (False, True)
+        got = d.pack_video_header(3, 480, 640, 29.97)
+        want = oracle.best_variants().pack_video_header(3, 480, 640, 29.97)
+        assert (np.asarray(got) == want).all() and got[20:].tolist() == [30, 0, 0, 0, 0, 0, 0, 0]
+        assert d.unpack_video_header(got) == (28, (3, 480, 640, 30.0))
+    finally:
+        pkg.set_format_variants(False, False)
+    assert d.pack_video_header(3, 480, 640, 29.97).tobytes() == oracle.port.pack_video_header(3, 480, 640, 29.97).tobytes()

@@ -171,6 +171,38 @@ def test_many_depths_per_warp_aligned(codec, W, H):
     roundtrip_check(codec, np.stack([rand_frame(rng, W, H, "classes") for _ in range(3)]))
 
 
+@pytest.mark.parametrize("W,H", [(64, 40), (1001, 43), (2048, 16), (4096, 8), (2049, 9), (10, 10)])
+def test_invert_endian_variant_matches_the_reference_built_with_the_macro(dropin, W, H):
+    """DBDE_INVERT_ENDIAN (dbde_util.cpp:15-19,24-27,246-270): tile rows byte-reversed on the way in and
+    out; every kernel family (wide, aligned, contiguous odd, segmented odd) against the unmodified
+    reference compiled with the macro.  Also through the C++ drop-in, which follows the process setting."""
+    V = oracle.best_variants()
+    rng = np.random.default_rng(W + 31 * H)
+    fr = np.stack([rand_frame(rng, W, H, ["classes", "noise", "classes"][i % 3]) for i in range(3)])
+    want, sizes = V.pack_frames(fr, 9)
+    c = pkg.Codec(0)
+    try:
+        c.set_invert_endian(True)
+        got, offs = c.encode_host(fr, 9)
+        assert (got == want).all()
+        dec, status, _ = c.decode_host(want, offs[:3], W, H)
+        assert (status == 0).all() and (dec == fr).all()
+        plain, _ = ORA.pack_frames(fr, 9)
+        assert not np.array_equal(plain, want)
+    finally:
+        c.close()
+    try:
+        pkg.set_format_variants(True, True)
+        rec = dropin.pack_frame(9, fr[0])
+        assert (rec == want[:int(sizes[0])]).all()
+        used, hdr, img = dropin.unpack_frame(rec, W, H)
+        assert used == int(sizes[0]) and hdr == (2, 9, 0) and (img == fr[0]).all()
+        assert (dropin.pack_video_header(3, H, W, 59.94) == V.pack_video_header(3, H, W, 59.94)).all()
+    finally:
+        pkg.set_format_variants(False, False)
+    assert (dropin.pack_frame(9, fr[0]) == ORA.pack_frame(9, fr[0])).all()
+
+
 def test_every_depth_class_uniform(codec):
     """a whole frame at each depth 0..8 (uniform-depth warps hit the worst staging strides)"""
     rng = np.random.default_rng(11)

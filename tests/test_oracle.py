@@ -8,7 +8,7 @@ import pytest
 
 import oracle
 import synth
-from conftest import golden_random_frames
+from conftest import golden_random_frames, rand_frame
 
 CODECS = [("port", oracle.port)] + ([("ref", oracle.ref)] if oracle.ref is not None else [])
 ids = [c[0] for c in CODECS]
@@ -174,3 +174,26 @@ def test_depth8_stores_pixel_minus_min(name, cd):
     tile = (np.arange(64).reshape(8, 8) * 3 + 50).astype(np.uint8)      # range 189 -> depth 8, min 50
     r, pay = cd.pack_8x8(tile)
     assert r == 0x832 and pay[:3].tolist() == [0, 3, 6] and len(pay) == 64
+
+
+# ------------------------------------------------------------------ the reference's compile-time variants
+def test_port_variants_match_the_reference_built_with_both_macros():
+    """DBDE_INVERT_ENDIAN + DBDE_HZ_AS_INTEGER (dbde_util.cpp:15-19,203-204,352-353): the port's run-time
+    switches against the unmodified reference compiled with the two macros (oracle/_ref)."""
+    if oracle.ref_variants is None:
+        pytest.skip("oracle/_ref/libdbde_ref_variants.so not built")
+    pv, rv = oracle.port_variants(), oracle.ref_variants
+    rng = np.random.default_rng(77)
+    differs = False
+    for W, H in [(8, 8), (10, 10), (17, 23), (64, 40), (1001, 24)]:
+        for style in ("classes", "noise", "flat"):
+            fr = np.stack([rand_frame(rng, W, H, style) for _ in range(2)])
+            a, sa = pv.pack_frames(fr, 5)
+            b, sb = rv.pack_frames(fr, 5)
+            assert list(sa) == list(sb) and (a == b).all(), (W, H, style)
+            differs |= not np.array_equal(a, oracle.port.pack_frames(fr, 5)[0])
+            assert (pv.unpack_frames(a, W, H, 2)[0] == fr).all() and (rv.unpack_frames(a, W, H, 2)[0] == fr).all()
+    assert differs, "the variant must change the payload bytes"
+    hv = rv.pack_video_header(3, 480, 640, 29.97)
+    assert (pv.pack_video_header(3, 480, 640, 29.97) == hv).all() and hv[20:].tolist() == [30, 0, 0, 0, 0, 0, 0, 0]
+    assert pv.unpack_video_header(hv) == rv.unpack_video_header(hv) == (28, (3, 480, 640, 30.0))
