@@ -34,8 +34,8 @@ KIND = "micro"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=1000, help="frames per GPU per step")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -62,9 +62,10 @@ def workload_config(a, extra=None):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """Samples SM clock, power and throttle reasons through NVML every ~2 ms on a thread (the timed
-    region is tens of milliseconds: nvidia-smi -lms cannot resolve it).  stop(t0, t1) keeps only the
-    samples taken inside the timed region [t0, t1] (time.perf_counter)."""
+    """Samples SM clock and throttle reasons through NVML as fast as the calls return (~1 ms; power
+    every 8th sample) on a thread -- the timed region is tens to hundreds of milliseconds, which
+    nvidia-smi -lms cannot resolve.  stop(t0, t1) keeps only the samples taken inside the timed
+    region [t0, t1] (time.perf_counter)."""
 
     def __init__(self, index):
         import threading
@@ -85,14 +86,17 @@ class ClockSampler:
 
     def _run(self):
         nv = self.nv
+        power, k = 0.0, 0
         while not self._stop.is_set():
             try:
-                self.samples.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
-                                     nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0,
+                if k % 8 == 0:
+                    power = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                k += 1
+                self.samples.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), power,
                                      nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.0005)
 
     def stop(self, t0, t1):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -146,13 +150,14 @@ def run_reference(a):
     for _ in range(a.warmup):
         cpu_reference_rates(frames, threads, target_s=0.2)
     t0 = time.time()
+    target = max(0.1, min(0.5, 15.0 / max(a.steps, 1)))       # ~30 s of timed CPU work in total, whatever K is
     for _ in range(a.steps):
-        per.append(cpu_reference_rates(frames, threads, target_s=0.5))
+        per.append(cpu_reference_rates(frames, threads, target_s=target))
     wall = time.time() - t0
     val = float(np.mean([p["value"] for p in per]))
     enc = float(np.mean([p["encode_fps"] for p in per]))
     dec = float(np.mean([p["decode_fps"] for p in per]))
-    sample = "%d frames of the same workload, dbde_pack_frame then dbde_unpack_frame, ~0.5 s per direction per step" % nsample
+    sample = "%d frames of the same workload, dbde_pack_frame then dbde_unpack_frame, ~%.2f s per direction per step" % (nsample, target)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1000.0 * wall / max(a.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
