@@ -203,6 +203,50 @@ def test_invert_endian_variant_matches_the_reference_built_with_the_macro(dropin
     assert (dropin.pack_frame(9, fr[0]) == ORA.pack_frame(9, fr[0])).all()
 
 
+def test_empty_batch_and_bad_arguments(codec):
+    """nframes == 0 is a no-op that succeeds; nonsense dimensions and short output buffers are refused
+    with an error code instead of a launch (the reference has no such checks: SURVEY 8b 'no bounds
+    checking anywhere' -- the C ABI adds capacity arguments, the drop-in layer keeps the contract)"""
+    got, offs = codec.encode_host(np.zeros((0, 16, 16), dtype=np.uint8), 0)
+    assert len(got) == 0 and offs.tolist() == [0]
+    dec, status, _ = codec.decode_host(np.zeros(0, dtype=np.uint8), np.zeros(0, dtype=np.uint64), 16, 16)
+    assert dec.shape == (0, 16, 16) and len(status) == 0
+    lib, h = codec.lib, codec.h
+    buf = np.zeros(4096, dtype=np.uint8)
+    offs = np.zeros(4, dtype=np.uint64)
+    assert lib.dbde_b200_encode_host(h, buf.ctypes.data, 0, 8, 0, 1, buf.ctypes.data, 4096, offs.ctypes.data) != 0
+    assert lib.dbde_b200_encode_host(h, buf.ctypes.data, 8, -1, 0, 1, buf.ctypes.data, 4096, offs.ctypes.data) != 0
+    assert lib.dbde_b200_encode_host(h, buf.ctypes.data, 8, 8, 0, -1, buf.ctypes.data, 4096, offs.ctypes.data) != 0
+    fr = np.arange(64, dtype=np.uint8).reshape(1, 8, 8)           # depth 6: a 32 + 2 + 48 = 82-byte record
+    assert lib.dbde_b200_encode_host(h, fr.ctypes.data, 8, 8, 0, 1, buf.ctypes.data, 40, offs.ctypes.data) != 0
+    assert b"" != lib.dbde_b200_last_error()
+    roundtrip_check(codec, fr)                                    # the context is still usable after refusals
+
+
+@pytest.mark.parametrize("W,H,N", [(8200, 9, 2), (16384, 24, 1), (32768, 8, 1), (16400, 17, 1), (1, 3000, 2), (3000, 1, 2),
+                                   (8192, 4096, 1)])
+def test_very_wide_tall_and_big_frames(codec, W, H, N):
+    """many band segments per band (w up to 4096 tiles = 16 segments), degenerate 1-pixel-wide/high
+    frames, and one 32 MiB frame (131 072 partitions-worth of look-back in one chain)"""
+    if W * H > 1 << 22:
+        fr = synth.gen_frames("mix", N, W, H, f0=2)
+    else:
+        rng = np.random.default_rng(W ^ H)
+        fr = np.stack([rand_frame(rng, W, H, "classes") for _ in range(N)])
+    roundtrip_check(codec, fr, first_index=2 ** 63 + 5)
+
+
+def test_many_tiny_frames(codec):
+    """20 000 README-sized frames in one batch: one partition per frame, chunking and slot compaction
+    at a record size (<= 296 bytes) far below any staging granularity"""
+    N = 20000
+    rng = np.random.default_rng(5)
+    fr = rng.integers(0, 256, (N, 10, 10), dtype=np.uint8)
+    fr[::3] &= 0x0F
+    fr[::7] = 200
+    roundtrip_check(codec, fr, first_index=123456789)
+
+
 def test_every_depth_class_uniform(codec):
     """a whole frame at each depth 0..8 (uniform-depth warps hit the worst staging strides)"""
     rng = np.random.default_rng(11)
