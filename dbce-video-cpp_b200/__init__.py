@@ -28,7 +28,7 @@ ST_BAD_WORD_COUNT, ST_DEPTH_TOO_BIG, ST_TRUNCATED = 8, 16, 32
 C_SYMBOLS = [
     "dbde_b200_create", "dbde_b200_destroy", "dbde_b200_last_error", "dbde_b200_device_count",
     "dbde_b200_frame_record_bound", "dbde_b200_slot_stride", "dbde_b200_stream_bound", "dbde_b200_device_alloc", "dbde_b200_device_free",
-    "dbde_b200_host_alloc", "dbde_b200_host_free", "dbde_b200_memcpy_h2d", "dbde_b200_memcpy_d2h",
+    "dbde_b200_host_alloc", "dbde_b200_host_free", "dbde_b200_host_register", "dbde_b200_host_unregister", "dbde_b200_memcpy_h2d", "dbde_b200_memcpy_d2h",
     "dbde_b200_encode_device", "dbde_b200_decode_device", "dbde_b200_encode_host", "dbde_b200_decode_host",
     "dbde_b200_encode_host_sharded", "dbde_b200_decode_host_sharded",
     "dbde_b200_index_stream", "dbde_b200_set_chunk_frames", "dbde_b200_kernel_launches",
@@ -100,6 +100,8 @@ def load():
     lib.dbde_b200_index_stream.restype = C.c_long
     lib.dbde_b200_index_stream.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_long]
     lib.dbde_b200_set_chunk_frames.argtypes = [C.c_void_p, C.c_int]
+    lib.dbde_b200_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    lib.dbde_b200_host_unregister.argtypes = [C.c_void_p]
     lib.dbde_b200_set_format_variants.restype = None
     lib.dbde_b200_set_format_variants.argtypes = [C.c_int, C.c_int]
     lib.dbde_b200_get_format_variants.restype = None

@@ -235,6 +235,20 @@ extern "C" int dbde_b200_host_free(void *p) {
     CK(cudaFreeHost(p));
     return 0;
 }
+// Page-locks memory the CALLER owns (malloc, new, a mapped file ...) so the host entry points copy
+// it by DMA instead of through the driver's pageable staging.  The caller must unregister before
+// freeing it; the library never registers anything behind the caller's back (a cached registration
+// of memory that was freed and re-mapped would DMA into the wrong pages).
+extern "C" int dbde_b200_host_register(void *p, size_t bytes) {
+    if (!p || !bytes) return fail(DBDE_B200_E_INVALID, "host_register: bad argument");
+    CK(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return 0;
+}
+extern "C" int dbde_b200_host_unregister(void *p) {
+    if (!p) return fail(DBDE_B200_E_INVALID, "host_unregister: bad argument");
+    CK(cudaHostUnregister(p));
+    return 0;
+}
 extern "C" int dbde_b200_memcpy_h2d(dbde_b200_ctx *c, void *dst, const void *src, size_t bytes) {
     if (!c) return fail(DBDE_B200_E_INVALID, "memcpy_h2d: bad argument");
     CK(cudaSetDevice(c->device));
@@ -502,6 +516,11 @@ extern "C" int dbde_b200_decode_host(dbde_b200_ctx *c, const uint8_t *stream_hos
         if (b1 - b0 > need_a) need_a = b1 - b0;
     }
     need_a += 64;
+    // Size the stream staging for the worst case of this geometry, not for this call's records: a caller
+    // that decodes frame after frame (the drop-in dbde_unpack_frame, the file walker) would otherwise
+    // pay a cudaFree + cudaMalloc every time a record is larger than any before it.
+    const size_t bound_a = dbde_b200_stream_bound(W, H, chunk) + 64;
+    if (need_a < bound_a) need_a = bound_a;
     const size_t need_b = px * chunk + 32;
     const int ns = nchunks < c->nslots ? nchunks : c->nslots;
     for (int i = 0; i < ns; i++) {

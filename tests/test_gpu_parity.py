@@ -236,6 +236,30 @@ def test_very_wide_tall_and_big_frames(codec, W, H, N):
     roundtrip_check(codec, fr, first_index=2 ** 63 + 5)
 
 
+def test_caller_owned_buffers_can_be_page_locked(codec, dropin):
+    """dbde_b200_host_register / _unregister on memory the caller owns (what a maintainer adds around a
+    long-lived frame buffer so the drop-in calls copy by DMA): same bytes, and the buffers work again after
+    unregistering"""
+    W, H = 520, 264
+    fr = synth.gen_frames("mix", 1, W, H, f0=9)[0].copy()
+    rec_buf = np.zeros(codec.lib.dbde_b200_frame_record_bound(W, H), dtype=np.uint8)
+    assert codec.lib.dbde_b200_host_register(fr.ctypes.data, fr.nbytes) == 0
+    assert codec.lib.dbde_b200_host_register(rec_buf.ctypes.data, rec_buf.nbytes) == 0
+    try:
+        want = ORA.pack_frame(3, fr)
+        for _ in range(3):
+            got = dropin.pack_frame(3, fr)
+            assert (got == want).all()
+        offs = np.zeros(2, dtype=np.uint64)
+        codec.encode_host_raw(fr.ctypes.data, W, H, 3, 1, rec_buf.ctypes.data, rec_buf.nbytes, offs.ctypes.data)
+        assert int(offs[1]) == len(want) and (rec_buf[:len(want)] == want).all()
+    finally:
+        assert codec.lib.dbde_b200_host_unregister(fr.ctypes.data) == 0
+        assert codec.lib.dbde_b200_host_unregister(rec_buf.ctypes.data) == 0
+    assert (dropin.pack_frame(3, fr) == want).all()
+    assert codec.lib.dbde_b200_host_register(None, 16) != 0 and codec.lib.dbde_b200_host_unregister(None) != 0
+
+
 def test_many_tiny_frames(codec):
     """20 000 README-sized frames in one batch: one partition per frame, chunking and slot compaction
     at a record size (<= 296 bytes) far below any staging granularity"""
