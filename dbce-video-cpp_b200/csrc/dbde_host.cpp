@@ -217,6 +217,7 @@ struct WalkerSide {
     size_t next = 0, have = 0;
     bool eof = false;
     int batch = 1;
+    bool registered = false;            // walker->buffer is page-locked (dbde_b200_host_register)
 };
 std::mutex g_wmx;
 std::unordered_map<uint8_t *, WalkerSide *> g_wside;      // keyed by walker->buffer
@@ -279,6 +280,8 @@ dbde_file_walker dbde_start_file_walk(const char *name, int frames_buffered, vid
         return w;
     }
     s->hdrs.resize(frames_buffered);
+    // the file buffer is ours from malloc to free: page-lock it so the records go to the GPU by DMA
+    s->registered = dbde_b200_host_register(w.buffer, N) == 0;
     std::lock_guard<std::mutex> lk(g_wmx);
     g_wside[w.buffer] = s;
     return w;
@@ -328,6 +331,7 @@ void dbde_end_file_walk(dbde_file_walker *w) {
             std::lock_guard<std::mutex> lk(g_wmx);
             auto it = g_wside.find(w->buffer);
             if (it != g_wside.end()) {
+                if (it->second->registered) dbde_b200_host_unregister(w->buffer);
                 if (it->second->frames) dbde_b200_host_free(it->second->frames);
                 delete it->second;
                 g_wside.erase(it);
