@@ -362,6 +362,31 @@ __device__ __forceinline__ void pack_rows_var(const uint32_t (&q)[16], int k, ui
     }
 }
 
+// pack for a warp whose tiles all have depth <= 2 (low-entropy video: flat background, 1-2 bits of
+// noise).  A byte-weighted dot product squeezes 4 pixels in ONE instruction when the weights
+// 1, 2^k, 2^2k, 2^3k fit in bytes (IDP.4A; k <= 2), and the fields of both depths are then joined by
+// the same three multiply-adds with lane-varying multipliers: no per-depth specialisation runs, no
+// divergence.  px = (pixel - min); wp = the tile's 8-byte aligned staging address.  Lanes with k == 0
+// compute zeros and store nothing.
+__device__ __forceinline__ void pack_low_depths(const uint32_t (&px)[16], int k, uint8_t *wp) {
+    const uint32_t wts = k == 2 ? 0x40100401u : 0x08040201u;
+    const uint32_t m1 = 1u << (4 * k), m2 = 1u << (8 * k);
+    uint32_t r[4];                                   // r[m] = tile rows 2m, 2m+1 = 16 pixels = 16k bits
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const uint32_t q0 = __dp4a(px[4 * m], wts, 0u), q1 = __dp4a(px[4 * m + 1], wts, 0u);
+        const uint32_t q2 = __dp4a(px[4 * m + 2], wts, 0u), q3 = __dp4a(px[4 * m + 3], wts, 0u);
+        r[m] = (q0 + q1 * m1) + (q2 + q3 * m1) * m2;
+    }
+    const uint32_t addr = smem_u32(wp);
+    if (k == 2) {
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(r[0]), "r"(r[1]) : "memory");
+        asm volatile("st.shared.v2.u32 [%0+8], {%1, %2};" ::"r"(addr), "r"(r[2]), "r"(r[3]) : "memory");
+    } else if (k == 1) {
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(r[0] + (r[1] << 16)), "r"(r[2] + (r[3] << 16)) : "memory");
+    }
+}
+
 // unaligned-safe shared loads for the generic (odd width / odd offset) paths
 __device__ __forceinline__ uint32_t lds_u32_unaligned(const uint8_t *p) {
     uint32_t a = smem_u32(p);

@@ -402,8 +402,12 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
             // ---- stage (4): pack (p - min) into k U64 words, staged linearly in the dead pixel bytes
             // a warp holding many different depths would run concat_fields<K> once per depth: from
             // DBDE_VAR_MIN_DEPTHS distinct non-zero depths on, the depth-agnostic row packer is shorter
-            const bool many_depths = __popc(__reduce_or_sync(0xffffffffu, (1u << k) >> 1)) >= DBDE_ENC_VAR_MIN_DEPTHS;
-            if (k > 0) {
+            const uint32_t kinds = __reduce_or_sync(0xffffffffu, (1u << k) >> 1);      // bit d-1 set: some tile has depth d
+            const bool many_depths = __popc(kinds) >= DBDE_ENC_VAR_MIN_DEPTHS;
+            if ((kinds & ~3u) == 0u) {
+                // low-entropy warp (every depth <= 2): one dot-product squeeze for all lanes, no specialisation
+                if (kinds) pack_low_depths(px, k, stage_out + 8 * off);
+            } else if (k > 0) {
                 const uint32_t c1 = (1u << k) - 256u, c2 = (1u << (2 * k)) - 65536u;
                 uint32_t q[16];
 #pragma unroll
