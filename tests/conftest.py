@@ -45,3 +45,17 @@ def golden_random_frames(golden):
         img = rand_frame(rng, c["W"], c["H"], c["style"])
         out.append((c, img))
     return out
+
+
+def build_example(name="batched_roundtrip"):
+    """Compile examples/<name>.cpp against the in-tree library (g++ only: the example is host C++ over the
+    C ABI and the reference-compatible header).  -> path of the executable"""
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "dbce-video-cpp_b200")
+    exe = os.path.join(tempfile.mkdtemp(prefix="dbde_example_"), name)
+    subprocess.run(["g++", "-O2", "-std=c++14", "-Wall", "-Werror", "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "examples", name + ".cpp"), "-L" + lib, "-ldbde_b200", "-Wl,-rpath," + lib, "-o", exe],
+                   check=True)
+    return exe

@@ -98,3 +98,18 @@ def test_video_header_hz_as_integer_variant_is_host_only(lib):
     finally:
         pkg.set_format_variants(False, False)
     assert d.pack_video_header(3, 480, 640, 29.97).tobytes() == oracle.port.pack_video_header(3, 480, 640, 29.97).tobytes()
+
+
+def test_integration_example_builds_and_refuses_to_run_without_a_gpu(lib):
+    """examples/batched_roundtrip.cpp is INTEGRATION.md's batched binding, complete: it must compile and
+    link against the two public headers alone, and without a B200 it must stop with the library's
+    message rather than produce a file through some other path"""
+    import subprocess
+    import tempfile
+    from conftest import build_example
+    exe = build_example()
+    out = os.path.join(tempfile.mkdtemp(), "x.dbde")
+    r = subprocess.run([exe, out, "64", "64", "2"], capture_output=True, text=True)
+    import torch
+    if not torch.cuda.is_available():
+        assert r.returncode != 0 and "no CPU fallback" in r.stderr

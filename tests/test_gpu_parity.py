@@ -260,6 +260,36 @@ def test_caller_owned_buffers_can_be_page_locked(codec, dropin):
     assert codec.lib.dbde_b200_host_register(None, 16) != 0 and codec.lib.dbde_b200_host_unregister(None) != 0
 
 
+def test_integration_example_writes_the_references_bytes():
+    """examples/batched_roundtrip.cpp (the C++ binding of INTEGRATION.md section 2): built with g++ on the
+    box, run, and its .dbde file compared with what the reference's dbde_pack_video_header +
+    dbde_pack_frame write for the same frames"""
+    import subprocess
+    from conftest import build_example
+    exe = build_example()
+    W, H, N = 333, 251, 7
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "example.dbde")
+        r = subprocess.run([exe, path, str(W), str(H), str(N)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "round trip exact" in r.stdout
+        got = np.fromfile(path, dtype=np.uint8)
+    # the example's frame generator, restated
+    z = np.uint64(42)
+    a, c = np.uint64(6364136223846793005), np.uint64(1442695040888963407)
+    n = N * H * W
+    zs = np.empty(n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        for i in range(n):
+            z = z * a + c
+            zs[i] = z
+    f, y, x = np.meshgrid(np.arange(N), np.arange(H), np.arange(W), indexing="ij")
+    fr = ((((x + 3 * f) >> 3) + ((y >> 4) & 15) + ((zs.reshape(N, H, W) >> np.uint64(60)) & np.uint64(3)).astype(np.int64)) & 255).astype(np.uint8)
+    want, _ = ORA.pack_frames(fr, 0)
+    hdr = ORA.pack_video_header(3, H, W, 25.0)
+    assert len(got) == 28 + len(want) and (got[:28] == hdr).all() and (got[28:] == want).all()
+
+
 def test_many_tiny_frames(codec):
     """20 000 README-sized frames in one batch: one partition per frame, chunking and slot compaction
     at a record size (<= 296 bytes) far below any staging granularity"""
