@@ -290,6 +290,29 @@ def test_integration_example_writes_the_references_bytes():
     assert len(got) == 28 + len(want) and (got[:28] == hdr).all() and (got[28:] == want).all()
 
 
+def test_random_geometries(codec):
+    """120 seeded random cases: any width/height from 1 to 300 (and a few wide ones), 1-5 frames, every
+    content style, random first index -- sweeps W % 8, H % 8, bands per partition and tiles per warp
+    through both the aligned and the odd-size kernels"""
+    rng = np.random.default_rng(20261018)
+    for case in range(120):
+        if case % 10 == 9:
+            W, H = int(rng.integers(2040, 2300)), int(rng.integers(1, 40))
+        else:
+            W, H = int(rng.integers(1, 301)), int(rng.integers(1, 301))
+        N = int(rng.integers(1, 6))
+        styles = ["classes", "noise", "flat", "low"]
+        frames = []
+        for i in range(N):
+            st = styles[int(rng.integers(0, 4))]
+            if st == "low":
+                img = (int(rng.integers(0, 250)) + (rng.integers(0, 256, (H, W)) & int(rng.integers(0, 4)))).astype(np.uint8)
+            else:
+                img = rand_frame(rng, W, H, st)
+            frames.append(img)
+        roundtrip_check(codec, np.stack(frames), first_index=int(rng.integers(0, 2 ** 62)))
+
+
 def test_many_tiny_frames(codec):
     """20 000 README-sized frames in one batch: one partition per frame, chunking and slot compaction
     at a record size (<= 296 bytes) far below any staging granularity"""
