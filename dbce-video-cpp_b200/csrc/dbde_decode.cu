@@ -505,6 +505,10 @@ __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecPa
 // Measured on mix/micro/noise/low 1001x1003: 3 input stages (2 CTAs/SM) -11 %; spinning instead of sleeping in
 // the store warp: no change; without the bulk store: -3 % time; without the shared-memory row stores:
 // -30 % -- the unaligned row stores (narrow pieces, 2-way bank conflicts), not the TMA traffic, are the cost.
+// Tried instead: tile warps store aligned 8-byte rows at a 16-byte-multiple pitch and the store warp
+// re-aligns row by row (2 x LDS.128 + 4 funnel shifts + one 16-byte global store per chunk): correct, but
+// 2x SLOWER (0.85 vs 0.43 ms per 1000 frames) -- ~90 instructions per image row on ONE warp that gets a
+// seventh of its scheduler; spread over the tile warps it would cost what the narrow stores cost now.
 constexpr int kStgStages = 2;                                    // input stages
 constexpr int kStgThreads = kTilesPerPart + 64;
 constexpr int kStgOutBytes = 64 * kTilesPerPart + 128;           // image of <= 16 KiB + the 16-byte shift, 128-byte multiple
