@@ -31,7 +31,7 @@ C_SYMBOLS = [
     "dbde_b200_host_alloc", "dbde_b200_host_free", "dbde_b200_host_register", "dbde_b200_host_unregister", "dbde_b200_memcpy_h2d", "dbde_b200_memcpy_d2h",
     "dbde_b200_encode_device", "dbde_b200_decode_device", "dbde_b200_encode_host", "dbde_b200_decode_host",
     "dbde_b200_encode_host_sharded", "dbde_b200_decode_host_sharded",
-    "dbde_b200_index_stream", "dbde_b200_set_chunk_frames", "dbde_b200_kernel_launches",
+    "dbde_b200_index_stream", "dbde_b200_validate_device", "dbde_b200_validate_host", "dbde_b200_set_chunk_frames", "dbde_b200_kernel_launches",
     "dbde_b200_set_format_variants", "dbde_b200_get_format_variants", "dbde_b200_set_invert_endian",
     "dbde_b200_writer_open", "dbde_b200_writer_append", "dbde_b200_writer_close",
     "dbde_b200_reader_open", "dbde_b200_reader_next", "dbde_b200_reader_close", "dbde_b200_file_last_error",
@@ -248,6 +248,19 @@ class Codec:
     def decode_host_raw(self, stream_ptr, stream_bytes, offs_ptr, W, H, N, frames_ptr, status_ptr, index_ptr=None):
         self._ck(self.lib.dbde_b200_decode_host(self.h, stream_ptr, stream_bytes, offs_ptr, W, H, N, frames_ptr,
                                                 status_ptr, index_ptr), "decode_host")
+
+    def validate_host(self, stream, offsets, W, H):
+        """GPU validation without decoding -> (status[N], indices[N])"""
+        stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        N = len(offsets)
+        status = np.zeros(N, dtype=np.uint32)
+        index = np.zeros(N, dtype=np.uint64)
+        self.lib.dbde_b200_validate_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                     C.c_void_p, C.c_void_p]
+        self._ck(self.lib.dbde_b200_validate_host(self.h, stream.ctypes.data, stream.nbytes, offsets.ctypes.data, W, H, N,
+                                                  status.ctypes.data, index.ctypes.data), "validate_host")
+        return status, index
 
     def index_stream(self, stream, W, H, max_frames=1 << 20):
         stream = np.ascontiguousarray(stream, dtype=np.uint8)

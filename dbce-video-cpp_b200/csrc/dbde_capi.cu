@@ -315,12 +315,12 @@ extern "C" int dbde_b200_encode_device(dbde_b200_ctx *c, const uint8_t *frames_d
     return 0;
 }
 
-extern "C" int dbde_b200_decode_device(dbde_b200_ctx *c, const uint8_t *stream_dev, size_t stream_bytes,
-                                       const uint64_t *frame_offsets_dev, int W, int H, int nframes,
-                                       uint8_t *frames_dev, uint32_t *status_dev, uint64_t *indices_dev,
-                                       void *stream) {
+// scan_only: run the validation pre-pass alone (status + indices, no pixels): dbde_b200_validate_*
+static int decode_device_impl(dbde_b200_ctx *c, const uint8_t *stream_dev, size_t stream_bytes,
+                              const uint64_t *frame_offsets_dev, int W, int H, int nframes, uint8_t *frames_dev,
+                              uint32_t *status_dev, uint64_t *indices_dev, void *stream, bool scan_only) {
     if (!c || !dims_ok(W, H, nframes) ||
-        (nframes > 0 && (!stream_dev || !frame_offsets_dev || !frames_dev || !status_dev)))
+        (nframes > 0 && (!stream_dev || !frame_offsets_dev || (!frames_dev && !scan_only) || !status_dev)))
         return fail(DBDE_B200_E_INVALID, "decode_device: bad argument");
     if (nframes == 0) return 0;
     CK(cudaSetDevice(c->device));
@@ -344,9 +344,29 @@ extern "C" int dbde_b200_decode_device(dbde_b200_ctx *c, const uint8_t *stream_d
     P.nparts = (unsigned)nparts;
     P.flags = c->invert_endian ? kFlagInvertRows : 0u;
     CK(launch_decode_scan(P, st));
+    c->launches += 1;
+    if (scan_only) return 0;
     CK(launch_decode(P, fast, c->num_sms, st));
-    c->launches += 2;
+    c->launches += 1;
     return 0;
+}
+
+extern "C" int dbde_b200_decode_device(dbde_b200_ctx *c, const uint8_t *stream_dev, size_t stream_bytes,
+                                       const uint64_t *frame_offsets_dev, int W, int H, int nframes,
+                                       uint8_t *frames_dev, uint32_t *status_dev, uint64_t *indices_dev,
+                                       void *stream) {
+    return decode_device_impl(c, stream_dev, stream_bytes, frame_offsets_dev, W, H, nframes, frames_dev, status_dev,
+                              indices_dev, stream, false);
+}
+
+// The indexer's optional GPU validation: the checks dbde_unpack_image makes before it
+// touches the image (dbde_util.cpp:295-303: nb == wh, nm == wh, sum(depth) == n64; plus tag, depth <= 8,
+// bounds), for every record of a device-resident stream, without decoding a pixel.
+extern "C" int dbde_b200_validate_device(dbde_b200_ctx *c, const uint8_t *stream_dev, size_t stream_bytes,
+                                         const uint64_t *frame_offsets_dev, int W, int H, int nframes,
+                                         uint32_t *status_dev, uint64_t *indices_dev, void *stream) {
+    return decode_device_impl(c, stream_dev, stream_bytes, frame_offsets_dev, W, H, nframes, nullptr, status_dev,
+                              indices_dev, stream, true);
 }
 
 // ------------------------------------------------------------------ host-buffer hot path
@@ -491,11 +511,11 @@ extern "C" int dbde_b200_encode_host(dbde_b200_ctx *c, const uint8_t *frames_hos
     return 0;
 }
 
-extern "C" int dbde_b200_decode_host(dbde_b200_ctx *c, const uint8_t *stream_host, size_t stream_bytes,
-                                     const uint64_t *frame_offsets_host, int W, int H, int nframes,
-                                     uint8_t *frames_host, uint32_t *status_host, uint64_t *indices_host) {
+static int decode_host_impl(dbde_b200_ctx *c, const uint8_t *stream_host, size_t stream_bytes,
+                            const uint64_t *frame_offsets_host, int W, int H, int nframes, uint8_t *frames_host,
+                            uint32_t *status_host, uint64_t *indices_host, bool scan_only) {
     if (!c || !dims_ok(W, H, nframes) ||
-        (nframes > 0 && (!stream_host || !frame_offsets_host || !frames_host || !status_host)))
+        (nframes > 0 && (!stream_host || !frame_offsets_host || (!frames_host && !scan_only) || !status_host)))
         return fail(DBDE_B200_E_INVALID, "decode_host: bad argument");
     if (nframes == 0) return 0;
     CK(cudaSetDevice(c->device));
@@ -521,7 +541,7 @@ extern "C" int dbde_b200_decode_host(dbde_b200_ctx *c, const uint8_t *stream_hos
     // pay a cudaFree + cudaMalloc every time a record is larger than any before it.
     const size_t bound_a = dbde_b200_stream_bound(W, H, chunk) + 64;
     if (need_a < bound_a) need_a = bound_a;
-    const size_t need_b = px * chunk + 32;
+    const size_t need_b = scan_only ? 0 : px * chunk + 32;
     const int ns = nchunks < c->nslots ? nchunks : c->nslots;
     for (int i = 0; i < ns; i++) {
         int rc = ensure_slot(c, c->slots[i], need_a, need_b, 0, chunk);
@@ -533,6 +553,7 @@ extern "C" int dbde_b200_decode_host(dbde_b200_ctx *c, const uint8_t *stream_hos
     auto finish = [&](int ci) -> int {
         HostSlot &s = c->slots[ci % ns];
         CK(cudaEventSynchronize(s.ev));
+        if (scan_only) return 0;
         int run0 = 0;
         for (int i = 0; i <= s.n; i++) {
             const bool ok = i < s.n && status_host[s.first + i] == 0;
@@ -556,8 +577,8 @@ extern "C" int dbde_b200_decode_host(dbde_b200_ctx *c, const uint8_t *stream_hos
         for (int i = 0; i < s.n; i++) s.h_off[i] = frame_offsets_host[s.first + i] - b0;
         CK(cudaMemcpyAsync(s.d_off, s.h_off, 8 * (size_t)s.n, cudaMemcpyHostToDevice, s.st));
         CK(cudaMemcpyAsync(s.d_a + delta, stream_host + b0, b1 - b0, cudaMemcpyHostToDevice, s.st));
-        rc_all = dbde_b200_decode_device(c, s.d_a + delta, b1 - b0, s.d_off, W, H, s.n, s.d_b, s.d_status,
-                                         s.d_index, s.st);
+        rc_all = decode_device_impl(c, s.d_a + delta, b1 - b0, s.d_off, W, H, s.n, s.d_b, s.d_status, s.d_index, s.st,
+                                    scan_only);
         if (rc_all) break;
         CK(cudaMemcpyAsync(status_host + s.first, s.d_status, 4 * (size_t)s.n, cudaMemcpyDeviceToHost, s.st));
         if (indices_host)
@@ -570,6 +591,22 @@ extern "C" int dbde_b200_decode_host(dbde_b200_ctx *c, const uint8_t *stream_hos
     for (auto &s : c->slots)
         if (s.st) cudaStreamSynchronize(s.st);
     return rc_all;
+}
+
+extern "C" int dbde_b200_decode_host(dbde_b200_ctx *c, const uint8_t *stream_host, size_t stream_bytes,
+                                     const uint64_t *frame_offsets_host, int W, int H, int nframes,
+                                     uint8_t *frames_host, uint32_t *status_host, uint64_t *indices_host) {
+    return decode_host_impl(c, stream_host, stream_bytes, frame_offsets_host, W, H, nframes, frames_host, status_host,
+                            indices_host, false);
+}
+
+// dbde_b200_validate_device for a stream in host memory: the records cross PCIe once, nothing comes
+// back but 4 (+8) bytes per frame.
+extern "C" int dbde_b200_validate_host(dbde_b200_ctx *c, const uint8_t *stream_host, size_t stream_bytes,
+                                       const uint64_t *frame_offsets_host, int W, int H, int nframes,
+                                       uint32_t *status_host, uint64_t *indices_host) {
+    return decode_host_impl(c, stream_host, stream_bytes, frame_offsets_host, W, H, nframes, nullptr, status_host,
+                            indices_host, true);
 }
 
 // ------------------------------------------------------------------ multi-GPU sharding

@@ -139,6 +139,19 @@ DBDE_B200_API int dbde_b200_decode_host_sharded(dbde_b200_ctx **ctxs, int nctx, 
 DBDE_B200_API long dbde_b200_index_stream(const uint8_t *stream_host, size_t stream_bytes, int W, int H,
                                           uint64_t *frame_offsets, long max_frames);
 
+/* Optional GPU validation for the indexer: every check dbde_unpack_image makes before
+ * it touches the image (dbde_util.cpp:295-303: nb == wh, nm == wh, sum(depth) == n64), plus the frame
+ * tag (:335), depth <= 8 and bounds, for each record -- status[i] = 0 or DBDE_B200_ST_* bits exactly as
+ * the decoders report them -- without decoding a pixel.  indices (may be NULL) receives the frame
+ * indices.  _device: stream and outputs in device memory, asynchronous on `stream`; _host: host memory,
+ * synchronous (the records cross PCIe once, 4 (+8) bytes per frame come back). */
+DBDE_B200_API int dbde_b200_validate_device(dbde_b200_ctx *ctx, const uint8_t *stream_dev, size_t stream_bytes,
+                                            const uint64_t *frame_offsets_dev, int W, int H, int nframes,
+                                            uint32_t *status_dev, uint64_t *indices_dev, void *stream);
+DBDE_B200_API int dbde_b200_validate_host(dbde_b200_ctx *ctx, const uint8_t *stream_host, size_t stream_bytes,
+                                          const uint64_t *frame_offsets_host, int W, int H, int nframes,
+                                          uint32_t *status_host, uint64_t *indices_host);
+
 /* ---- .dbde files: 28-byte video header + frame records back to back ------------- */
 /* The container the reference's walker reads (dbde_util.cpp:362-426; dbde_start_file_walk /
  * dbde_walk_a_file / dbde_end_file_walk in include/dbde_util.h remain available as the drop-in).

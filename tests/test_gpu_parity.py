@@ -313,6 +313,37 @@ def test_random_geometries(codec):
         roundtrip_check(codec, np.stack(frames), first_index=int(rng.integers(0, 2 ** 62)))
 
 
+def test_gpu_validation_without_decoding(codec):
+    """dbde_b200_validate_host: the reference's accept/reject decision for every record
+    (dbde_util.cpp:295-303,335), taken on the GPU without decoding; must agree with what the decoder and
+    the oracle say, for good and for damaged records"""
+    W, H, N = 1001, 43, 12
+    wh = ((W + 7) // 8) * ((H + 7) // 8)
+    fr = synth.gen_frames("mix", N, W, H)
+    stream, sizes = ORA.pack_frames(fr, 40)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    status, index = codec.validate_host(stream, offs[:N], W, H)
+    assert (status == 0).all() and index.tolist() == list(range(40, 40 + N))
+    bad = stream.copy()
+    bad[int(offs[1]) + 20] += 1                 # nb != wh
+    bad[int(offs[2]) + 24 + wh] += 1            # nm != wh
+    bad[int(offs[5]) + 28 + 2 * wh] ^= 1        # n64 != sum(depth)
+    bad[int(offs[7])] = 9                       # frame tag != 2
+    bad[int(offs[9]) + 24 + 3] = 9              # a depth byte > 8
+    status, _ = codec.validate_host(bad, offs[:N], W, H)
+    _, dstatus, _ = codec.decode_host(bad, offs[:N], W, H)
+    assert status.tolist() == dstatus.tolist()
+    assert status[1] == pkg.ST_BAD_DEPTH_COUNT and status[2] == pkg.ST_BAD_MIN_COUNT and status[5] == pkg.ST_BAD_WORD_COUNT
+    assert status[7] == pkg.ST_BAD_FRAME_HEADER and status[9] & pkg.ST_DEPTH_TOO_BIG
+    for i in range(N):
+        o_used, o_hdr, _ = ORA.unpack_frame(bad[int(offs[i]):int(offs[i + 1])], W, H)
+        if i != 9:                               # depth > 8 is the documented deviation (reference: unpinned)
+            assert (status[i] == 0) == (o_hdr[0] == 2), i
+    launches = codec.launches()
+    codec.validate_host(stream, offs[:N], W, H)
+    assert codec.launches() - launches == 1      # the scan pre-pass alone
+
+
 def test_many_tiny_frames(codec):
     """20 000 README-sized frames in one batch: one partition per frame, chunking and slot compaction
     at a record size (<= 296 bytes) far below any staging granularity"""
