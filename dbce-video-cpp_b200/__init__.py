@@ -31,6 +31,8 @@ C_SYMBOLS = [
     "dbde_b200_host_alloc", "dbde_b200_host_free", "dbde_b200_host_register", "dbde_b200_host_unregister", "dbde_b200_memcpy_h2d", "dbde_b200_memcpy_d2h",
     "dbde_b200_encode_device", "dbde_b200_decode_device", "dbde_b200_encode_host", "dbde_b200_decode_host",
     "dbde_b200_encode_host_sharded", "dbde_b200_decode_host_sharded",
+    "dbde_b200_frame_record_bound16", "dbde_b200_slot_stride16", "dbde_b200_encode16_device", "dbde_b200_decode16_device",
+    "dbde_b200_encode16_host", "dbde_b200_decode16_host",
     "dbde_b200_index_stream", "dbde_b200_validate_device", "dbde_b200_validate_host", "dbde_b200_set_chunk_frames", "dbde_b200_kernel_launches",
     "dbde_b200_set_format_variants", "dbde_b200_get_format_variants", "dbde_b200_set_invert_endian",
     "dbde_b200_writer_open", "dbde_b200_writer_append", "dbde_b200_writer_close",
@@ -100,6 +102,17 @@ def load():
     lib.dbde_b200_index_stream.restype = C.c_long
     lib.dbde_b200_index_stream.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_long]
     lib.dbde_b200_set_chunk_frames.argtypes = [C.c_void_p, C.c_int]
+    for fn in (lib.dbde_b200_frame_record_bound16, lib.dbde_b200_slot_stride16):
+        fn.restype = C.c_size_t
+        fn.argtypes = [C.c_int, C.c_int]
+    lib.dbde_b200_encode16_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_size_t,
+                                            C.c_void_p]
+    lib.dbde_b200_decode16_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                            C.c_void_p, C.c_void_p]
+    lib.dbde_b200_encode16_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_size_t,
+                                              C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dbde_b200_decode16_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dbde_b200_host_register.argtypes = [C.c_void_p, C.c_size_t]
     lib.dbde_b200_host_unregister.argtypes = [C.c_void_p]
     lib.dbde_b200_set_format_variants.restype = None
@@ -248,6 +261,30 @@ class Codec:
     def decode_host_raw(self, stream_ptr, stream_bytes, offs_ptr, W, H, N, frames_ptr, status_ptr, index_ptr=None):
         self._ck(self.lib.dbde_b200_decode_host(self.h, stream_ptr, stream_bytes, offs_ptr, W, H, N, frames_ptr,
                                                 status_ptr, index_ptr), "decode_host")
+
+    # ---- DBDE16, the 16-bit extension
+    def encode16_host(self, frames, first_index=0):
+        """frames (N,H,W) u16 -> (stream bytes, offsets[N+1])"""
+        frames = np.ascontiguousarray(frames, dtype=np.uint16)
+        N, H, W = frames.shape
+        cap = int(self.lib.dbde_b200_slot_stride16(W, H)) * max(N, 1) + 16
+        out = np.empty(cap, dtype=np.uint8)
+        offs = np.zeros(N + 1, dtype=np.uint64)
+        self._ck(self.lib.dbde_b200_encode16_host(self.h, frames.ctypes.data, W, H, first_index, N, out.ctypes.data, cap,
+                                                  offs.ctypes.data), "encode16_host")
+        return out[:int(offs[N])].copy(), offs
+
+    def decode16_host(self, stream, offsets, W, H, fill=None):
+        """-> (frames (N,H,W) u16, status[N], indices[N]); rejected frames keep `fill`"""
+        stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        N = len(offsets)
+        frames = np.zeros((N, H, W), dtype=np.uint16) if fill is None else np.full((N, H, W), fill, dtype=np.uint16)
+        status = np.zeros(N, dtype=np.uint32)
+        index = np.zeros(N, dtype=np.uint64)
+        self._ck(self.lib.dbde_b200_decode16_host(self.h, stream.ctypes.data, stream.nbytes, offsets.ctypes.data, W, H, N,
+                                                  frames.ctypes.data, status.ctypes.data, index.ctypes.data), "decode16_host")
+        return frames, status, index
 
     def validate_host(self, stream, offsets, W, H):
         """GPU validation without decoding -> (status[N], indices[N])"""

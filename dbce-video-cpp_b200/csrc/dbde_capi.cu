@@ -609,6 +609,169 @@ extern "C" int dbde_b200_validate_host(dbde_b200_ctx *c, const uint8_t *stream_h
                             indices_host, true);
 }
 
+// ------------------------------------------------------------------ DBDE16
+extern "C" size_t dbde_b200_frame_record_bound16(int W, int H) {
+    const size_t wh = (size_t)((W + 7) / 8) * ((H + 7) / 8);
+    return 32 + 3 * wh + 128 * wh;
+}
+extern "C" size_t dbde_b200_slot_stride16(int W, int H) { return (dbde_b200_frame_record_bound16(W, H) + 15) & ~(size_t)15; }
+
+extern "C" int dbde_b200_encode16_device(dbde_b200_ctx *c, const uint16_t *frames_dev, int W, int H, uint64_t first_index,
+                                         int nframes, uint8_t *out_dev, size_t out_capacity, size_t slot_stride,
+                                         uint64_t *frame_offsets_dev, uint64_t *frame_sizes_dev, void *stream) {
+    if (!c || !dims_ok(W, H, nframes) || (nframes > 0 && (!frames_dev || !out_dev || !frame_offsets_dev || !frame_sizes_dev)) ||
+        ((uintptr_t)frames_dev & 1))
+        return fail(DBDE_B200_E_INVALID, "encode16_device: bad argument");
+    if (nframes == 0) return 0;
+    if (slot_stride == 0) slot_stride = dbde_b200_slot_stride16(W, H);
+    if (slot_stride < dbde_b200_frame_record_bound16(W, H))
+        return fail(DBDE_B200_E_INVALID, "encode16_device: slot_stride < dbde_b200_frame_record_bound16()");
+    if (out_capacity < slot_stride * (size_t)nframes)
+        return fail(DBDE_B200_E_CAPACITY, "encode16_device: out_capacity < nframes * slot_stride");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Enc16Params P;
+    P.W = W; P.H = H; P.w = (W + 7) / 8; P.h = (H + 7) / 8; P.wh = P.w * P.h;
+    P.ppf = (P.wh + 255) / 256;
+    const unsigned long long nparts = (unsigned long long)nframes * P.ppf;
+    if (nparts >= 0xFFFFFFF0ull) return fail(DBDE_B200_E_INVALID, "encode16_device: batch too large");
+    const size_t sbytes = 128 + 8 * (size_t)nparts;
+    int rc = grow(&c->enc_scratch, &c->enc_scratch_bytes, sbytes);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(c->enc_scratch, 0, sbytes, st));
+    P.frames = frames_dev; P.out = out_dev; P.slot_stride = slot_stride;
+    P.frame_offsets = frame_offsets_dev; P.frame_sizes = frame_sizes_dev;
+    P.ticket = (unsigned int *)c->enc_scratch;
+    P.desc = (uint64_t *)((uint8_t *)c->enc_scratch + 128);
+    P.first_index = first_index; P.nframes = nframes; P.nparts = (unsigned)nparts;
+    P.aligned = (W % 8 == 0) && (((uintptr_t)frames_dev & 15) == 0);
+    CK(launch_encode16(P, c->num_sms, st));
+    c->launches += 1;
+    return 0;
+}
+
+extern "C" int dbde_b200_decode16_device(dbde_b200_ctx *c, const uint8_t *stream_dev, size_t stream_bytes,
+                                         const uint64_t *frame_offsets_dev, int W, int H, int nframes, uint16_t *frames_dev,
+                                         uint32_t *status_dev, uint64_t *indices_dev, void *stream) {
+    if (!c || !dims_ok(W, H, nframes) || (nframes > 0 && (!stream_dev || !frame_offsets_dev || !frames_dev || !status_dev)) ||
+        ((uintptr_t)frames_dev & 1))
+        return fail(DBDE_B200_E_INVALID, "decode16_device: bad argument");
+    if (nframes == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Dec16Params P;
+    P.W = W; P.H = H; P.w = (W + 7) / 8; P.h = (H + 7) / 8; P.wh = P.w * P.h;
+    P.ppf = (P.wh + 255) / 256;
+    const unsigned long long nparts = (unsigned long long)nframes * P.ppf;
+    if (nparts >= 0xFFFFFFF0ull) return fail(DBDE_B200_E_INVALID, "decode16_device: batch too large");
+    const size_t sbytes = 4 * (size_t)nframes * ((size_t)(P.wh + 31) / 32 + 1);
+    int rc = grow(&c->dec_scratch, &c->dec_scratch_bytes, sbytes);
+    if (rc) return rc;
+    P.stream = stream_dev; P.stream_bytes = stream_bytes; P.frame_offsets = frame_offsets_dev;
+    P.frames = frames_dev; P.status = status_dev; P.indices = indices_dev;
+    P.wprefix = (uint32_t *)c->dec_scratch;
+    P.nframes = nframes; P.nparts = (unsigned)nparts;
+    P.aligned = (W % 8 == 0) && (((uintptr_t)frames_dev & 15) == 0);
+    CK(launch_decode16_scan(P, st));
+    CK(launch_decode16(P, c->num_sms, st));
+    c->launches += 2;
+    return 0;
+}
+
+// Host-buffer forms: one staged batch at a time (H2D, kernels, record compaction, D2H), synchronous.
+// The 8-bit path's chunk pipeline is not replicated for the extension.
+extern "C" int dbde_b200_encode16_host(dbde_b200_ctx *c, const uint16_t *frames_host, int W, int H, uint64_t first_index,
+                                       int nframes, uint8_t *out_host, size_t out_capacity, uint64_t *frame_offsets_host) {
+    if (!c || !dims_ok(W, H, nframes) || (nframes > 0 && (!frames_host || !out_host || !frame_offsets_host)))
+        return fail(DBDE_B200_E_INVALID, "encode16_host: bad argument");
+    if (frame_offsets_host) frame_offsets_host[0] = 0;
+    if (nframes == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    const size_t px2 = 2 * (size_t)W * H, stride = dbde_b200_slot_stride16(W, H);
+    int chunk = (int)((128u << 20) / (px2 ? px2 : 1));
+    if (chunk < 1) chunk = 1;
+    if (chunk > nframes) chunk = nframes;
+    HostSlot &s = c->slots[0];
+    int rc = ensure_slot(c, s, px2 * chunk + 32, stride * chunk + 64, stride * chunk + 64, chunk);
+    if (rc) return rc;
+    size_t pos = 0;
+    for (int first = 0; first < nframes; first += chunk) {
+        const int n = nframes - first < chunk ? nframes - first : chunk;
+        CK(cudaMemcpyAsync(s.d_a, frames_host + (size_t)first * W * H, px2 * n, cudaMemcpyHostToDevice, s.st));
+        rc = dbde_b200_encode16_device(c, (const uint16_t *)s.d_a, W, H, first_index + first, n, s.d_b, stride * n, stride, s.d_off,
+                                       s.d_size, s.st);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(s.h_size, s.d_size, 8 * (size_t)n, cudaMemcpyDeviceToHost, s.st));
+        CK(launch_compact(s.d_b, stride, s.d_size, n, s.d_c, s.st));
+        c->launches += 1;
+        CK(cudaStreamSynchronize(s.st));
+        uint64_t total = 0;
+        for (int i = 0; i < n; i++) {
+            frame_offsets_host[first + i] = pos + total;
+            total += s.h_size[i];
+        }
+        if (pos + total > out_capacity) return fail(DBDE_B200_E_CAPACITY, "encode16_host: out_capacity too small");
+        CK(cudaMemcpyAsync(out_host + pos, s.d_c, total, cudaMemcpyDeviceToHost, s.st));
+        CK(cudaStreamSynchronize(s.st));
+        pos += total;
+    }
+    frame_offsets_host[nframes] = pos;
+    return 0;
+}
+
+extern "C" int dbde_b200_decode16_host(dbde_b200_ctx *c, const uint8_t *stream_host, size_t stream_bytes,
+                                       const uint64_t *frame_offsets_host, int W, int H, int nframes, uint16_t *frames_host,
+                                       uint32_t *status_host, uint64_t *indices_host) {
+    if (!c || !dims_ok(W, H, nframes) || (nframes > 0 && (!stream_host || !frame_offsets_host || !frames_host || !status_host)))
+        return fail(DBDE_B200_E_INVALID, "decode16_host: bad argument");
+    if (nframes == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    for (int i = 0; i < nframes; i++) {
+        const uint64_t end = i + 1 < nframes ? frame_offsets_host[i + 1] : stream_bytes;
+        if (frame_offsets_host[i] > end || end > stream_bytes)
+            return fail(DBDE_B200_E_INVALID, "decode16_host: frame offsets must ascend within the stream");
+    }
+    const size_t px2 = 2 * (size_t)W * H;
+    int chunk = (int)((128u << 20) / (px2 ? px2 : 1));
+    if (chunk < 1) chunk = 1;
+    if (chunk > nframes) chunk = nframes;
+    size_t need_a = 0;
+    for (int first = 0; first < nframes; first += chunk) {
+        const int n = nframes - first < chunk ? nframes - first : chunk;
+        const uint64_t b0 = frame_offsets_host[first], b1 = first + n < nframes ? frame_offsets_host[first + n] : stream_bytes;
+        if (b1 - b0 > need_a) need_a = b1 - b0;
+    }
+    const size_t bound_a = dbde_b200_slot_stride16(W, H) * chunk;
+    if (need_a < bound_a) need_a = bound_a;
+    HostSlot &s = c->slots[0];
+    int rc = ensure_slot(c, s, need_a + 64, px2 * chunk + 32, 0, chunk);
+    if (rc) return rc;
+    for (int first = 0; first < nframes; first += chunk) {
+        const int n = nframes - first < chunk ? nframes - first : chunk;
+        const uint64_t b0 = frame_offsets_host[first], b1 = first + n < nframes ? frame_offsets_host[first + n] : stream_bytes;
+        for (int i = 0; i < n; i++) s.h_off[i] = frame_offsets_host[first + i] - b0;
+        CK(cudaMemcpyAsync(s.d_off, s.h_off, 8 * (size_t)n, cudaMemcpyHostToDevice, s.st));
+        CK(cudaMemcpyAsync(s.d_a, stream_host + b0, b1 - b0, cudaMemcpyHostToDevice, s.st));
+        rc = dbde_b200_decode16_device(c, s.d_a, b1 - b0, s.d_off, W, H, n, (uint16_t *)s.d_b, s.d_status, s.d_index, s.st);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(status_host + first, s.d_status, 4 * (size_t)n, cudaMemcpyDeviceToHost, s.st));
+        if (indices_host) CK(cudaMemcpyAsync(indices_host + first, s.d_index, 8 * (size_t)n, cudaMemcpyDeviceToHost, s.st));
+        CK(cudaStreamSynchronize(s.st));
+        int run0 = 0;                                     // rejected frames keep the caller's pixels
+        for (int i = 0; i <= n; i++) {
+            const bool ok = i < n && status_host[first + i] == 0;
+            if (!ok) {
+                if (i > run0)
+                    CK(cudaMemcpyAsync(frames_host + (size_t)(first + run0) * W * H, s.d_b + px2 * run0, px2 * (size_t)(i - run0),
+                                       cudaMemcpyDeviceToHost, s.st));
+                run0 = i + 1;
+            }
+        }
+        CK(cudaStreamSynchronize(s.st));
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------ multi-GPU sharding
 // contiguous frame ranges, one host thread per context; there is no cross-GPU exchange on the
 // data path, the host only prefix-sums the shard sizes

@@ -47,6 +47,33 @@ enum : uint32_t {
     kStTruncated = 32,       // record runs past the end of the stream buffer
 };
 
+// ---- DBDE16, the 16-bit extension (dbde16.cu): partitions of 256 consecutive tiles
+struct Enc16Params {
+    const uint16_t *frames;     // nframes * W * H u16, tightly packed, device
+    uint8_t *out;               // record f at out + f * slot_stride
+    uint64_t slot_stride;       // >= 32 + 131 * wh
+    uint64_t *frame_offsets, *frame_sizes;
+    uint64_t *desc;             // nparts look-back descriptors (index f*ppf + q), zeroed
+    unsigned int *ticket;       // zeroed
+    uint64_t first_index;
+    int W, H, w, h, wh, ppf, nframes, aligned;   // aligned: rows can be moved 16 bytes at a time
+    unsigned nparts;
+};
+struct Dec16Params {
+    const uint8_t *stream;
+    uint64_t stream_bytes;
+    const uint64_t *frame_offsets;
+    uint16_t *frames;
+    uint32_t *status;
+    uint64_t *indices;          // or null
+    uint32_t *wprefix;          // nframes * (ceil(wh/32) + 1) exclusive word prefixes per 32-tile group
+    int W, H, w, h, wh, ppf, nframes, aligned;
+    unsigned nparts;
+};
+cudaError_t launch_encode16(const Enc16Params &P, int num_sms, cudaStream_t stream);
+cudaError_t launch_decode16_scan(const Dec16Params &P, cudaStream_t stream);
+cudaError_t launch_decode16(const Dec16Params &P, int num_sms, cudaStream_t stream);
+
 size_t enc_smem_bytes(const PartGeom &g);
 size_t dec_smem_bytes(const PartGeom &g);
 cudaError_t launch_encode(const EncParams &P, bool fast, int num_sms, cudaStream_t stream);

@@ -152,6 +152,31 @@ DBDE_B200_API int dbde_b200_validate_host(dbde_b200_ctx *ctx, const uint8_t *str
                                           const uint64_t *frame_offsets_host, int W, int H, int nframes,
                                           uint32_t *status_host, uint64_t *indices_host);
 
+/* ---- DBDE16: 16-bit frames -------------------------------------------------------
+ * The extension the format note hints at (reference README.md:65, "could expand size to handle higher
+ * bit depth images").  NOT in the reference code: the layout is defined here and restated by the test oracle
+ * ("DBDE16"): the reference's frame record with depths 0..16 and a two-byte little-endian minimum per tile,
+ *   I32 2 | U64 index | F64 0.0 | I32 wh | U8 depth[wh] | I32 2*wh | U16 min[wh] | I32 n64 | U64 words[n64]
+ * (a reader tells the layouts apart by the minimum plane's length).  A frame whose pixels fit in 8 bits
+ * gets exactly the 8-bit codec's depth plane and words.  Same conventions as the 8-bit entry points;
+ * frames are W*H U16 per frame, tightly packed; fastest when W % 8 == 0 and the frame buffer is 16-byte
+ * aligned.  The host forms stage one batch at a time (no chunk pipeline). */
+DBDE_B200_API size_t dbde_b200_frame_record_bound16(int W, int H);    /* 32 + 131*wh */
+DBDE_B200_API size_t dbde_b200_slot_stride16(int W, int H);
+DBDE_B200_API int dbde_b200_encode16_device(dbde_b200_ctx *ctx, const uint16_t *frames_dev, int W, int H,
+                                            uint64_t first_index, int nframes, uint8_t *out_dev, size_t out_capacity,
+                                            size_t slot_stride, uint64_t *frame_offsets_dev, uint64_t *frame_sizes_dev,
+                                            void *stream);
+DBDE_B200_API int dbde_b200_decode16_device(dbde_b200_ctx *ctx, const uint8_t *stream_dev, size_t stream_bytes,
+                                            const uint64_t *frame_offsets_dev, int W, int H, int nframes,
+                                            uint16_t *frames_dev, uint32_t *status_dev, uint64_t *indices_dev, void *stream);
+DBDE_B200_API int dbde_b200_encode16_host(dbde_b200_ctx *ctx, const uint16_t *frames_host, int W, int H,
+                                          uint64_t first_index, int nframes, uint8_t *out_host, size_t out_capacity,
+                                          uint64_t *frame_offsets_host);
+DBDE_B200_API int dbde_b200_decode16_host(dbde_b200_ctx *ctx, const uint8_t *stream_host, size_t stream_bytes,
+                                          const uint64_t *frame_offsets_host, int W, int H, int nframes,
+                                          uint16_t *frames_host, uint32_t *status_host, uint64_t *indices_host);
+
 /* ---- .dbde files: 28-byte video header + frame records back to back ------------- */
 /* The container the reference's walker reads (dbde_util.cpp:362-426; dbde_start_file_walk /
  * dbde_walk_a_file / dbde_end_file_walk in include/dbde_util.h remain available as the drop-in).

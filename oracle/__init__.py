@@ -182,6 +182,44 @@ def port_variants():
     return _Codec(lib, "oracle_")
 
 
+class _Codec16:
+    """DBDE16, the 16-bit extension: defined by the port only -- the reference has no
+    such code, so there is no compiled-reference counterpart ("parity unpinned")."""
+
+    def __init__(self, lib):
+        self.lib = lib
+        lib.oracle_frame_record_bound16.restype = C.c_size_t
+        lib.oracle_frame_record_bound16.argtypes = [C.c_int, C.c_int]
+        lib.oracle_pack_frames16.restype = C.c_size_t
+        lib.oracle_pack_frames16.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int, _u8p, _u64p]
+        lib.oracle_unpack_frame16.restype = C.c_size_t
+        lib.oracle_unpack_frame16.argtypes = [_u8p, C.c_int, C.c_int, C.c_void_p, _u64p]
+
+    def bound(self, W, H):
+        return int(self.lib.oracle_frame_record_bound16(W, H))
+
+    def pack_frames(self, frames, first_index=0):
+        """frames: (N,H,W) u16 -> (stream bytes, sizes[N])"""
+        frames = np.ascontiguousarray(frames, dtype=np.uint16)
+        N, H, W = frames.shape
+        out = np.zeros(N * self.bound(W, H) + 64, dtype=np.uint8)
+        sizes = np.zeros(N, dtype=np.uint64)
+        n = self.lib.oracle_pack_frames16(frames.ctypes.data, W, H, first_index, N, _ptr(out), sizes.ctypes.data_as(_u64p))
+        return out[:n].copy(), sizes
+
+    def unpack_frame(self, packed, W, H, fill=0xCDCD):
+        """-> (bytes consumed, (u64s, index, elapsed_ns), image u16)"""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        pad = np.concatenate([packed, np.zeros(160, dtype=np.uint8)])
+        img = np.full((H, W), fill, dtype=np.uint16)
+        hdr = np.zeros(3, dtype=np.uint64)
+        n = self.lib.oracle_unpack_frame16(_ptr(pad), W, H, img.ctypes.data, hdr.ctypes.data_as(_u64p))
+        return n, tuple(int(x) for x in hdr), img
+
+
+port16 = _Codec16(_port_lib)
+
+
 def best():
     """The strongest checker available: the compiled reference, else the port."""
     return ref if ref is not None else port

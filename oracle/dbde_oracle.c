@@ -262,3 +262,128 @@ ORACLE_API size_t oracle_unpack_frames(const uint8_t *stream, int W, int H, int 
     }
     return off;
 }
+
+/* ======================================================================================
+ * DBDE16 -- the 16-bit extension the format note hints at (README.md:65: "could expand
+ * size to handle higher bit depth images").  NOT IN THE REFERENCE CODE:
+ * there is nothing to be bit-exact with, so this restatement DEFINES the extension and is
+ * labelled "parity unpinned".  What pins it anyway (tests/test_oracle.py):
+ *   - embedding: a frame whose pixels all fit in 8 bits encodes to the same depth plane, the
+ *     same U64 words and the same minima as the reference-pinned 8-bit codec above -- only
+ *     the minimum plane is two bytes per tile;
+ *   - hand-computed words for small tiles, round trips, clamp padding as at dbde_util.cpp:105-135.
+ * Layout of a frame record (20-byte frame header unchanged, dbde_util.cpp:182-188):
+ *   I32 wh | U8 depth[wh] (0..16) | I32 2*wh | U16 min[wh] little-endian | I32 n64 | U64 words[n64]
+ * A tile's 64 values (pixel - min) are concatenated LSB-first, `depth` bits each, into `depth`
+ * little-endian U64 words -- the rule of README.md:54-56 with a wider pixel.  A reader tells
+ * the two layouts apart by the length of the minimum plane (wh vs 2*wh).
+ * ====================================================================================== */
+static int bit_length_u16(unsigned r) {
+    int k = 0;
+    while (r) { k++; r >>= 1; }
+    return k;
+}
+
+/* one clamp-padded tile; returns depth, *mn = minimum; writes 8*depth bytes */
+static int pack16_tile(const uint16_t *image, int stride, int rm, int dm, uint16_t *mn, uint8_t *target) {
+    uint16_t full[64];
+    for (int r = 0; r < 8; r++) {
+        int rr = r < dm ? r : dm - 1;
+        for (int c = 0; c < 8; c++) {
+            int cc = c < rm ? c : rm - 1;
+            full[8 * r + c] = image[(size_t)rr * stride + cc];
+        }
+    }
+    unsigned lo = 65535, hi = 0;
+    for (int i = 0; i < 64; i++) {
+        if (full[i] < lo) lo = full[i];
+        if (full[i] > hi) hi = full[i];
+    }
+    int k = bit_length_u16(hi - lo);
+    *mn = (uint16_t)lo;
+    if (k == 0) return 0;
+    memset(target, 0, (size_t)(8 * k));
+    for (int i = 0; i < 64; i++) {
+        unsigned q = (unsigned)full[i] - lo;
+        int bit = k * i;
+        for (int b = 0; b < k; b++, bit++)
+            if ((q >> b) & 1u) target[bit >> 3] |= (uint8_t)(1u << (bit & 7));
+    }
+    return k;
+}
+
+ORACLE_API size_t oracle_frame_record_bound16(int W, int H) {
+    size_t wh = (size_t)((W + 7) / 8) * ((H + 7) / 8);
+    return 32 + 3 * wh + 128 * wh;
+}
+
+/* image: H x W u16, tightly packed rows.  Returns the record size (20-byte header included). */
+ORACLE_API size_t oracle_pack_frame16(uint64_t index, const uint16_t *image, int W, int H, uint8_t *target) {
+    int w = (W + 7) / 8, h = (H + 7) / 8, wh = w * h;
+    size_t sz = oracle_pack_frame_header(2, index, 0, target);
+    uint8_t *t = target + sz;
+    uint8_t *bd = t + 4, *mi = t + 8 + wh, *words = t + 12 + 3 * (size_t)wh;
+    put_le(t, (uint32_t)wh, 4);
+    put_le(t + 4 + wh, (uint32_t)(2 * wh), 4);
+    uint32_t n64 = 0;
+    for (int ty = 0; ty < h; ty++)
+        for (int tx = 0; tx < w; tx++) {
+            int rm = W - 8 * tx; if (rm > 8) rm = 8;
+            int dm = H - 8 * ty; if (dm > 8) dm = 8;
+            uint16_t mn;
+            int k = pack16_tile(image + (size_t)8 * ty * W + 8 * tx, W, rm, dm, &mn, words + 8 * (size_t)n64);
+            *bd++ = (uint8_t)k;
+            put_le(mi, mn, 2); mi += 2;
+            n64 += (uint32_t)k;
+        }
+    put_le(t + 8 + 3 * (size_t)wh, n64, 4);
+    return sz + 12 + 3 * (size_t)wh + 8 * (size_t)n64;
+}
+
+/* Returns bytes consumed INCLUDING the 20-byte header; on a malformed block (nb != wh, nm != 2*wh,
+ * sum(depth) != n64, a depth > 16 -- the checks of dbde_util.cpp:295-303 carried over) out[0] =
+ * 0xFFFFFFFF, only 20 is returned and the image is untouched. */
+ORACLE_API size_t oracle_unpack_frame16(const uint8_t *packed, int W, int H, uint16_t *image, uint64_t out[3]) {
+    int w = (W + 7) / 8, h = (H + 7) / 8, wh = w * h;
+    size_t used = oracle_unpack_frame_header(packed, out);
+    const uint8_t *pack = packed + used;
+    int32_t nb = (int32_t)get_le(pack, 4); pack += 4;
+    if (nb != wh) { out[0] = 0xFFFFFFFFu; return used; }
+    const uint8_t *b = pack; pack += nb;
+    int32_t nm = (int32_t)get_le(pack, 4); pack += 4;
+    if (nm != 2 * wh) { out[0] = 0xFFFFFFFFu; return used; }
+    const uint8_t *m = pack; pack += nm;
+    int64_t n64 = (int64_t)(uint32_t)get_le(pack, 4); pack += 4;
+    for (int i = 0; i < wh; i++) {
+        if (b[i] > 16) { out[0] = 0xFFFFFFFFu; return used; }
+        n64 -= b[i];
+    }
+    if (n64 != 0) { out[0] = 0xFFFFFFFFu; return used; }
+    for (int ty = 0; ty < h; ty++)
+        for (int tx = 0; tx < w; tx++) {
+            int rm = W - 8 * tx; if (rm > 8) rm = 8;
+            int dm = H - 8 * ty; if (dm > 8) dm = 8;
+            int k = *b++;
+            unsigned mn = (unsigned)get_le(m, 2); m += 2;
+            for (int i = 0; i < 64; i++) {
+                unsigned q = 0;
+                int bit = k * i;
+                for (int bb = 0; bb < k; bb++, bit++) q |= ((pack[bit >> 3] >> (bit & 7)) & 1u) << bb;
+                int y = i >> 3, x = i & 7;
+                if (y < dm && x < rm) image[(size_t)(8 * ty + y) * W + 8 * tx + x] = (uint16_t)(q + mn);
+            }
+            pack += 8 * (size_t)k;
+        }
+    return (size_t)(pack - packed);
+}
+
+ORACLE_API size_t oracle_pack_frames16(const uint16_t *frames, int W, int H, uint64_t first_index, int n,
+                                       uint8_t *target, uint64_t *sizes) {
+    size_t off = 0;
+    for (int i = 0; i < n; i++) {
+        size_t s = oracle_pack_frame16(first_index + (uint64_t)i, frames + (size_t)i * W * H, W, H, target + off);
+        if (sizes) sizes[i] = s;
+        off += s;
+    }
+    return off;
+}

@@ -344,6 +344,73 @@ def test_gpu_validation_without_decoding(codec):
     assert codec.launches() - launches == 1      # the scan pre-pass alone
 
 
+# ------------------------------------------------------------------ DBDE16
+def rand_frame16(rng, W, H, style):
+    if style == "noise":
+        return rng.integers(0, 65536, (H, W), dtype=np.uint16)
+    if style == "flat":
+        return np.full((H, W), rng.integers(0, 65536), dtype=np.uint16)
+    if style == "byte":
+        return rng.integers(0, 256, (H, W)).astype(np.uint16)
+    th, tw = (H + 7) // 8, (W + 7) // 8
+    k = rng.integers(0, 17, (th, tw))
+    rg = (1 << k) - 1
+    mn = (rng.random((th, tw)) * (65536 - rg)).astype(np.int64)
+    big = (mn[:, :, None, None] + (rng.integers(0, 65536, (th, tw, 8, 8)) & rg[:, :, None, None]))
+    return big.transpose(0, 2, 1, 3).reshape(th * 8, tw * 8)[:H, :W].astype(np.uint16)
+
+
+@pytest.mark.parametrize("W,H", [(8, 8), (10, 10), (64, 64), (1, 1), (7, 9), (17, 23), (264, 24), (1001, 83), (2048, 16), (2056, 24),
+                                 (520, 520), (3000, 1), (1, 300)])
+def test_dbde16_matches_its_oracle(codec, W, H):
+    """16-bit frames: records byte-identical to oracle.port16 (the definition of the extension), decode
+    identical to the source, aligned (W % 8 == 0) and element-wise paths, every depth 0..16"""
+    rng = np.random.default_rng(W * 31 + H)
+    fr = np.stack([rand_frame16(rng, W, H, ["classes", "noise", "flat", "byte", "classes"][i % 5]) for i in range(5)])
+    want, sizes = oracle.port16.pack_frames(fr, 77)
+    got, offs = codec.encode16_host(fr, 77)
+    assert int(offs[5]) == len(want) and offs[:5].tolist() == [0] + np.cumsum(sizes).tolist()[:-1]
+    assert (got == want).all(), int(np.argmax(got != want))
+    dec, status, index = codec.decode16_host(want, offs[:5], W, H)
+    assert (status == 0).all() and index.tolist() == list(range(77, 82)) and (dec == fr).all()
+
+
+def test_dbde16_of_8_bit_content_is_the_8_bit_codec(codec):
+    """the embedding that ties the extension to the reference: pixels < 256 -> the reference's depth plane
+    and U64 words, minima widened to two bytes"""
+    W, H, N = 1001, 43, 3
+    wh = ((W + 7) // 8) * ((H + 7) // 8)
+    fr8 = synth.gen_frames("mix", N, W, H)
+    a, sa = ORA.pack_frames(fr8, 0)
+    b, offs = codec.encode16_host(fr8.astype(np.uint16), 0)
+    pa = 0
+    for i in range(N):
+        ra, rb = a[pa:pa + int(sa[i])], b[int(offs[i]):int(offs[i + 1])]
+        assert len(rb) == len(ra) + wh and (ra[:24 + wh] == rb[:24 + wh]).all() and (ra[28 + 2 * wh:] == rb[28 + 3 * wh:]).all()
+        assert (rb[28 + wh:28 + 3 * wh].view(np.uint16) == ra[28 + wh:28 + 2 * wh]).all()
+        pa += int(sa[i])
+
+
+def test_dbde16_rejects_damaged_records_and_many_frames(codec):
+    W, H, N = 136, 72, 40
+    wh = 17 * 9
+    rng = np.random.default_rng(8)
+    fr = np.stack([rand_frame16(rng, W, H, "classes") for _ in range(N)])
+    stream, sizes = oracle.port16.pack_frames(fr, 0)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    bad = stream.copy()
+    bad[int(offs[3]) + 24 + wh] ^= 1            # nm != 2*wh
+    bad[int(offs[9]) + 28 + 3 * wh] ^= 1        # n64 != sum(depth)
+    bad[int(offs[20]) + 24 + 5] = 17            # depth > 16
+    dec, status, _ = codec.decode16_host(bad, offs[:N], W, H, fill=0xCDCD)
+    assert status[3] == pkg.ST_BAD_MIN_COUNT and status[9] == pkg.ST_BAD_WORD_COUNT and status[20] & pkg.ST_DEPTH_TOO_BIG
+    for i in range(N):
+        if i in (3, 9, 20):
+            assert (dec[i] == 0xCDCD).all()
+        else:
+            assert status[i] == 0 and (dec[i] == fr[i]).all()
+
+
 def test_many_tiny_frames(codec):
     """20 000 README-sized frames in one batch: one partition per frame, chunking and slot compaction
     at a record size (<= 296 bytes) far below any staging granularity"""

@@ -197,3 +197,50 @@ def test_port_variants_match_the_reference_built_with_both_macros():
     hv = rv.pack_video_header(3, 480, 640, 29.97)
     assert (pv.pack_video_header(3, 480, 640, 29.97) == hv).all() and hv[20:].tolist() == [30, 0, 0, 0, 0, 0, 0, 0]
     assert pv.unpack_video_header(hv) == rv.unpack_video_header(hv) == (28, (3, 480, 640, 30.0))
+
+
+# ------------------------------------------------------------------ DBDE16 (not in the reference)
+def test_dbde16_embeds_the_8_bit_codec_and_round_trips():
+    """The 16-bit extension has no reference implementation ("parity unpinned"); what pins its definition:
+    a frame whose pixels fit in 8 bits must get the reference-pinned 8-bit codec's depth plane, minima and
+    U64 words (only the minimum plane is two bytes wide), true 16-bit frames must round-trip, and a
+    hand-computed tile must give the expected words."""
+    o16, o8 = oracle.port16, oracle.best()
+    rng = np.random.default_rng(3)
+    for W, H in [(8, 8), (10, 10), (17, 23), (64, 40), (1001, 24)]:
+        wh = ((W + 7) // 8) * ((H + 7) // 8)
+        for style in ("classes", "noise", "flat"):
+            fr8 = np.stack([rand_frame(rng, W, H, style) for _ in range(2)])
+            a, sa = o8.pack_frames(fr8, 5)
+            b, sb = o16.pack_frames(fr8.astype(np.uint16), 5)
+            pa = pb = 0
+            for i in range(2):
+                ra, rb = a[pa:pa + int(sa[i])], b[pb:pb + int(sb[i])]
+                assert int(sb[i]) == int(sa[i]) + wh
+                assert (ra[:24 + wh] == rb[:24 + wh]).all()                      # frame header, nb, depth plane
+                assert int.from_bytes(rb[24 + wh:28 + wh].tobytes(), "little") == 2 * wh
+                assert (rb[28 + wh:28 + 3 * wh].view(np.uint16) == ra[28 + wh:28 + 2 * wh]).all()
+                assert (ra[28 + 2 * wh:] == rb[28 + 3 * wh:]).all()              # n64 and every word
+                n, hdr, img = o16.unpack_frame(rb, W, H)
+                assert n == len(rb) and hdr == (2, 5 + i, 0) and (img == fr8[i]).all()
+                pa += int(sa[i]); pb += int(sb[i])
+    fr = rng.integers(0, 65536, (3, 37, 53), dtype=np.uint16)
+    s, sz = o16.pack_frames(fr, 0)
+    off = 0
+    for i in range(3):
+        n, hdr, img = o16.unpack_frame(s[off:off + int(sz[i])], 53, 37)
+        assert hdr[0] == 2 and (img == fr[i]).all()
+        off += n
+    # one tile by hand: min 1000, values 1000 + (i % 4) * 300 -> range 900 -> depth 10; pixel i at bits [10 i, 10 i + 10)
+    tile = (1000 + (np.arange(64) % 4) * 300).astype(np.uint16).reshape(1, 8, 8)
+    s, sz = o16.pack_frames(tile, 0)
+    assert s[24] == 10 and int.from_bytes(s[29:31].tobytes(), "little") == 1000 and int(sz[0]) == 32 + 3 + 80
+    bits = 0
+    for i in range(64):
+        bits |= int((i % 4) * 300) << (10 * i)
+    assert s[35:115].tobytes() == bits.to_bytes(80, "little")
+    # rejects: a damaged minimum-plane length, a depth above 16
+    bad = s.copy(); bad[25] ^= 1
+    assert o16.unpack_frame(bad, 8, 8)[1][0] == 0xFFFFFFFF
+    bad = s.copy(); bad[24] = 17
+    assert o16.unpack_frame(bad, 8, 8)[1][0] == 0xFFFFFFFF
