@@ -28,6 +28,16 @@ constexpr int kWordBytesPadded16 = kWordBytes16 + kWordBytes16 / 32 + 64;
 // dbde_pack_8x8_partial (dbde_util.cpp:105-135).
 __device__ __forceinline__ void load_tile16(const uint16_t *frame, int W, int H, int ty, int tx, bool aligned, uint32_t (&px)[32]) {
     const int rows_valid = min(8, H - 8 * ty), cols_valid = min(8, W - 8 * tx);
+    if (aligned && rows_valid == 8 && cols_valid == 8) {          // the common case: one pointer, eight 16-byte loads
+        const uint4 *row = reinterpret_cast<const uint4 *>(frame + (size_t)(8 * ty) * W + 8 * tx);
+        const size_t pitch = (size_t)W / 8;                       // in 16-byte units
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const uint4 v = __ldcs(row + r * pitch);
+            px[4 * r] = v.x; px[4 * r + 1] = v.y; px[4 * r + 2] = v.z; px[4 * r + 3] = v.w;
+        }
+        return;
+    }
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         const uint16_t *row = frame + (size_t)(8 * ty + min(r, rows_valid - 1)) * W + 8 * tx;
@@ -47,6 +57,13 @@ __device__ __forceinline__ void load_tile16(const uint16_t *frame, int W, int H,
 // crop as dbde_unpack_8x8_partial (dbde_util.cpp:281-289): only rows < H and columns < W are written
 __device__ __forceinline__ void store_tile16(uint16_t *frame, int W, int H, int ty, int tx, bool aligned, const uint32_t (&px)[32]) {
     const int rows_valid = min(8, H - 8 * ty), cols_valid = min(8, W - 8 * tx);
+    if (aligned && rows_valid == 8 && cols_valid == 8) {
+        uint4 *row = reinterpret_cast<uint4 *>(frame + (size_t)(8 * ty) * W + 8 * tx);
+        const size_t pitch = (size_t)W / 8;
+#pragma unroll
+        for (int r = 0; r < 8; r++) st_stream_v4u32(row + r * pitch, make_uint4(px[4 * r], px[4 * r + 1], px[4 * r + 2], px[4 * r + 3]));
+        return;
+    }
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         if (r >= rows_valid) break;
@@ -62,7 +79,7 @@ __device__ __forceinline__ void store_tile16(uint16_t *frame, int W, int H, int 
 }
 
 // ------------------------------------------------------------------ encoder
-__global__ void __launch_bounds__(kT16) dbde16_encode_kernel(const Enc16Params P) {
+__global__ void __launch_bounds__(kT16, 4) dbde16_encode_kernel(const Enc16Params P) {
     extern __shared__ __align__(16) uint8_t s_words[];
     __shared__ uint32_t s_ticket, s_wtot[kT16 / 32];
     __shared__ uint64_t s_excl;
@@ -122,20 +139,22 @@ __global__ void __launch_bounds__(kT16) dbde16_encode_kernel(const Enc16Params P
             const uint32_t m2 = mn * 0x00010001u, kk = 2u * (uint32_t)k;
             const uint32_t sbase = smem_u32(s_words);
             uint32_t unit = 2u * (wbase + incl - (uint32_t)k);                   // 32-bit unit inside the partition's words
-            uint64_t acc = 0;
-            uint32_t fill = 0;
+            uint32_t acc = 0, fill = 0;                                          // `fill` (< 32) valid low bits in acc
+            const uint32_t kmul = 1u << k;
 #pragma unroll
             for (int i = 0; i < 32; i++) {
                 const uint32_t d = px[i] - m2;                                   // no borrow: every pixel >= min
-                const uint32_t pair = (d & 0xffffu) | ((d >> 16) << k);
-                acc |= (uint64_t)pair << fill;
+                const uint32_t pair = (d >> 16) * kmul + (d & 0xffffu);          // 2k bits
+                const uint32_t lo = acc | (pair << fill);
+                const uint32_t hi = __funnelshift_l(pair, 0u, fill);             // what does not fit in 32 bits (0 when fill == 0)
                 fill += kk;
-                if (fill >= 32u) {
-                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(sbase + 4u * pad16(unit)), "r"((uint32_t)acc) : "memory");
-                    unit += 1u;
-                    acc >>= 32;
-                    fill -= 32u;
-                }
+                // a unit is complete: predicated store (no branch), carry the overflow
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.u32 p, %2, 32;\n\t@p st.shared.u32 [%0], %1;\n\t}"
+                             ::"r"(sbase + 4u * pad16(unit)), "r"(lo), "r"(fill) : "memory");
+                const bool full = fill >= 32u;
+                acc = full ? hi : lo;
+                unit += full ? 1u : 0u;
+                fill &= 31u;
             }
         }
         __syncthreads();                                      // words staged, s_excl published
