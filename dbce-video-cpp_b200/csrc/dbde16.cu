@@ -293,17 +293,29 @@ __global__ void __launch_bounds__(kT16) dbde16_decode_kernel(const Dec16Params P
         const uint32_t w0 = wp[g0], agg = wp[g1] - w0;
         // the partition's words, coalesced, into shared memory
         const uint8_t *src = rec + 32 + 3 * (size_t)P.wh + 8ull * w0;
+        // Padded layout (pad16): after every 32 units comes one padding unit, and that padding unit holds a
+        // COPY of the unit that follows it, so the reader's "this unit and the next" is always two adjacent loads.
         uint32_t *su = reinterpret_cast<uint32_t *>(s_words);
         if (((uintptr_t)src & 7) == 0) {
             for (uint32_t i = (uint32_t)tid; i < agg; i += kT16) {
                 const uint64_t v = __ldcs(reinterpret_cast<const uint64_t *>(src) + i);
-                su[pad16(2u * i)] = (uint32_t)v;
-                su[pad16(2u * i + 1u)] = (uint32_t)(v >> 32);
+                const uint32_t at = pad16(2u * i);                                  // units 2i and 2i+1 share a block of 32
+                su[at] = (uint32_t)v;
+                su[at + 1u] = (uint32_t)(v >> 32);
+                if (((2u * i) & 31u) == 0u && i > 0u) su[at - 1u] = (uint32_t)v;    // the copy in the padding slot before it
             }
         } else {
-            for (uint32_t i = (uint32_t)tid; i < 8u * agg; i += kT16) s_words[4u * pad16(i >> 2) + (i & 3u)] = src[i];
+            for (uint32_t i = (uint32_t)tid; i < 8u * agg; i += kT16) {
+                const uint32_t u = i >> 2;
+                s_words[4u * pad16(u) + (i & 3u)] = src[i];
+                if ((u & 31u) == 0u && u > 0u) s_words[4u * (pad16(u) - 1u) + (i & 3u)] = src[i];
+            }
         }
-        if (tid < 2) su[pad16(2u * agg + (uint32_t)tid)] = 0u;                    // the reader looks one unit ahead
+        if (tid < 2) {                                                            // the reader looks one unit past the end
+            const uint32_t u = 2u * agg + (uint32_t)tid;
+            su[pad16(u)] = 0u;
+            if ((u & 31u) == 0u && u > 0u) su[pad16(u) - 1u] = 0u;
+        }
         const int tile = (int)q * kT16 + tid;
         const bool valid = tile < P.wh;
         int k = 0;
@@ -324,8 +336,8 @@ __global__ void __launch_bounds__(kT16) dbde16_decode_kernel(const Dec16Params P
 #pragma unroll
             for (int i = 0; i < 32; i++) {
                 const uint32_t bit = kk * (uint32_t)i;                               // pair i: bits [2k i, 2k i + 2k)
-                const uint32_t unit = 2u * woff + (bit >> 5);
-                const uint32_t a = su[pad16(unit)], b = su[pad16(unit + 1u)];
+                const uint32_t at = pad16(2u * woff + (bit >> 5));
+                const uint32_t a = su[at], b = su[at + 1u];                          // the next unit, or its copy in the padding slot
                 const uint32_t v = __funnelshift_r(a, b, bit);                       // low 2k bits = the pair
                 px[i] = ((v & mk) | (((v >> k) & mk) << 16)) + m2;                    // + min, wrapping per pixel is impossible: <= 65535
             }
