@@ -12,7 +12,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -209,15 +211,30 @@ void dbde_unpack_8x8_partial(uint8_t depth, uint8_t minval, uint8_t *packed, siz
 // Same interface and field meanings as the reference (dbde_util.cpp:362-426) but: the buffer is
 // sized for the true worst-case record (32 + 66*wh, not npix + npix/8 + 32, which under-sizes
 // small odd frames), it is freed in dbde_end_file_walk, and frames are decoded on the GPU in
-// batches of `frames_buffered` and handed out one per call.
+// batches of `frames_buffered`.  A helper thread reads, indexes and decodes batch k+1 (fread -> page-locked
+// file buffer -> H2D -> kernels -> D2H into a pinned batch buffer) while the caller is still being handed
+// the frames of batch k, one per call: disk I/O and PCIe overlap the caller's own work.
 namespace {
 struct WalkerSide {
-    uint8_t *frames = nullptr;          // decoded batch (pinned: the D2H copy of a batch runs at PCIe speed)
-    std::vector<frame_header> hdrs;
-    size_t next = 0, have = 0;
-    bool eof = false;
-    int batch = 1;
-    bool registered = false;            // walker->buffer is page-locked (dbde_b200_host_register)
+    // file state: owned by the helper thread after start (the caller's struct only mirrors it)
+    FILE *f = nullptr;
+    uint8_t *buffer = nullptr;
+    size_t i = 0, n = 0, N = 0;
+    int W = 1, H = 1, batch = 1;
+    bool registered = false;            // `buffer` is page-locked (dbde_b200_host_register)
+    // two decoded batches (pinned: the D2H copy of a batch runs at PCIe speed)
+    uint8_t *frames[2] = {nullptr, nullptr};
+    std::vector<frame_header> hdrs[2];
+    size_t have[2] = {0, 0};
+    // hand-off: batch k lives in slot k & 1; the helper may run at most two batches ahead of `consumed`
+    std::mutex m;
+    std::condition_variable cv;
+    size_t produced = 0, consumed = 0;
+    bool finished = false, stop = false;
+    std::thread worker;
+    // caller side
+    size_t next = 0;                    // next frame of the current batch
+    bool holding = false;               // the caller is inside batch `consumed`
 };
 std::mutex g_wmx;
 std::unordered_map<uint8_t *, WalkerSide *> g_wside;      // keyed by walker->buffer
@@ -229,17 +246,74 @@ WalkerSide *side_of(const dbde_file_walker *w) {
 }
 
 // keep [i, n) topped up from the file (reference dbde_advance_file_buffer, :394-406)
-bool refill(dbde_file_walker *w) {
-    if (w->i > 0) {
-        if (w->i < w->n) memmove(w->buffer, w->buffer + w->i, w->n - w->i);
-        w->n -= w->i;
-        w->i = 0;
+bool refill(WalkerSide *s) {
+    if (s->i > 0) {
+        if (s->i < s->n) memmove(s->buffer, s->buffer + s->i, s->n - s->i);
+        s->n -= s->i;
+        s->i = 0;
     }
-    if (!feof(w->fptr)) {
-        w->n += fread(w->buffer + w->n, 1, w->N - w->n, w->fptr);
-        if (ferror(w->fptr)) return false;
+    if (!feof(s->f)) {
+        s->n += fread(s->buffer + s->n, 1, s->N - s->n, s->f);
+        if (ferror(s->f)) return false;
     }
     return true;
+}
+
+// decode the next batch of whole records into slot `b`; false = nothing more to hand out after this
+bool produce(WalkerSide *s, int b) {
+    s->have[b] = 0;
+    if (!refill(s)) return false;
+    std::vector<uint64_t> offs(s->batch + 1);
+    const long n = dbde_b200_index_stream(s->buffer + s->i, s->n - s->i, s->W, s->H, offs.data(), s->batch);
+    if (n <= 0) return false;                              // end of file (or a torn last record)
+    std::vector<uint32_t> status(n);
+    std::vector<uint64_t> index(n);
+    int rc = dbde_b200_decode_host(ctx(), s->buffer + s->i, (size_t)offs[n], offs.data(), s->W, s->H, (int)n, s->frames[b],
+                                   status.data(), index.data());
+    if (rc) die("dbde_walk_a_file", rc);
+    bool more = true;
+    for (long k = 0; k < n; k++) {
+        uint8_t *p = s->buffer + s->i + offs[k];
+        s->hdrs[b][k] = dbde_unpack_frame_header(&p);
+        if (status[k] != 0) s->hdrs[b][k].u64s = (uint32_t)-1;
+        s->have[b]++;
+        if (s->hdrs[b][k].u64s != 2) { more = false; break; }      // the reference stops at the first bad frame (:416)
+    }
+    s->i += (size_t)offs[n];
+    return more;
+}
+
+void worker_main(WalkerSide *s) {
+    for (;;) {
+        {
+            std::unique_lock<std::mutex> lk(s->m);
+            s->cv.wait(lk, [&] { return s->stop || s->produced - s->consumed < 2; });
+            if (s->stop) return;
+        }
+        const bool more = produce(s, (int)(s->produced & 1));
+        {
+            std::lock_guard<std::mutex> lk(s->m);
+            if (s->have[s->produced & 1] > 0) s->produced++;
+            if (!more) s->finished = true;
+        }
+        s->cv.notify_all();
+        if (!more) return;
+    }
+}
+
+void destroy_side(WalkerSide *s) {
+    {
+        std::lock_guard<std::mutex> lk(s->m);
+        s->stop = true;
+    }
+    s->cv.notify_all();
+    if (s->worker.joinable()) s->worker.join();
+    if (s->registered) dbde_b200_host_unregister(s->buffer);
+    for (int b = 0; b < 2; b++)
+        if (s->frames[b]) dbde_b200_host_free(s->frames[b]);
+    if (s->f) fclose(s->f);
+    free(s->buffer);
+    delete s;
 }
 }  // namespace
 
@@ -261,29 +335,35 @@ dbde_file_walker dbde_start_file_walk(const char *name, int frames_buffered, vid
     const size_t bound = dbde_b200_frame_record_bound((int)vh->width, (int)vh->height);
     const size_t N = bound * (size_t)frames_buffered + 64;
     if (N >= 0x7FFFFFFF) { fclose(f); return w; }
-    w.buffer = (uint8_t *)malloc(N);
-    if (!w.buffer) { fclose(f); return w; }
+    WalkerSide *s = new WalkerSide();
+    s->buffer = (uint8_t *)malloc(N);
+    if (!s->buffer) { fclose(f); delete s; return w; }
+    s->f = f;
+    s->N = N;
+    s->W = (int)vh->width;
+    s->H = (int)vh->height;
+    s->batch = frames_buffered;
+    const size_t px = (size_t)s->W * s->H;
+    for (int b = 0; b < 2; b++) {
+        if (dbde_b200_host_alloc((size_t)frames_buffered * px, (void **)&s->frames[b]) != 0) {
+            destroy_side(s);
+            return w;
+        }
+        s->hdrs[b].resize(frames_buffered);
+    }
+    // the file buffer is ours from malloc to free: page-lock it so the records go to the GPU by DMA
+    s->registered = dbde_b200_host_register(s->buffer, N) == 0;
+    // the caller's struct mirrors the reference's fields; the file itself now belongs to the helper thread
     w.fptr = f;
+    w.buffer = s->buffer;
     w.N = N;
     w.width = (int32_t)vh->width;
     w.height = (int32_t)vh->height;
-    w.n = fread(w.buffer, 1, N, f);
-    if (ferror(f)) { fclose(f); free(w.buffer); w.buffer = NULL; w.fptr = NULL; return w; }
-    WalkerSide *s = new WalkerSide();
-    s->batch = frames_buffered;
-    if (dbde_b200_host_alloc((size_t)frames_buffered * w.width * w.height, (void **)&s->frames) != 0) {
-        delete s;
-        fclose(f);
-        free(w.buffer);
-        w.buffer = NULL;
-        w.fptr = NULL;
-        return w;
+    {
+        std::lock_guard<std::mutex> lk(g_wmx);
+        g_wside[w.buffer] = s;
     }
-    s->hdrs.resize(frames_buffered);
-    // the file buffer is ours from malloc to free: page-lock it so the records go to the GPU by DMA
-    s->registered = dbde_b200_host_register(w.buffer, N) == 0;
-    std::lock_guard<std::mutex> lk(g_wmx);
-    g_wside[w.buffer] = s;
+    s->worker = std::thread(worker_main, s);
     return w;
 }
 
@@ -291,32 +371,24 @@ bool dbde_walk_a_file(dbde_file_walker *w, frame_header *fh, uint8_t *image) {
     if (!w || !w->fptr) return false;
     WalkerSide *s = side_of(w);
     if (!s) return false;
-    const size_t px = (size_t)w->width * w->height;
-    if (s->next == s->have) {
-        // decode the next batch of whole records that are in (or can be read into) the buffer
-        if (!refill(w)) { dbde_end_file_walk(w); return false; }
-        std::vector<uint64_t> offs(s->batch + 1);
-        const long n = dbde_b200_index_stream(w->buffer + w->i, w->n - w->i, w->width, w->height, offs.data(), s->batch);
-        if (n <= 0) return false;                          // end of file (or a torn last record)
-        std::vector<uint32_t> status(n);
-        std::vector<uint64_t> index(n);
-        int rc = dbde_b200_decode_host(ctx(), w->buffer + w->i, (size_t)offs[n], offs.data(), w->width, w->height,
-                                       (int)n, s->frames, status.data(), index.data());
-        if (rc) die("dbde_walk_a_file", rc);
-        s->have = 0;
-        for (long k = 0; k < n; k++) {
-            uint8_t *p = w->buffer + w->i + offs[k];
-            s->hdrs[k] = dbde_unpack_frame_header(&p);
-            if (status[k] != 0) s->hdrs[k].u64s = (uint32_t)-1;
-            s->have++;
-            if (status[k] != 0) break;                     // stop handing out frames at the first bad one
+    const size_t px = (size_t)s->W * s->H;
+    if (!s->holding || s->next == s->have[s->consumed & 1]) {
+        // hand the finished batch back to the helper and wait for the next one
+        std::unique_lock<std::mutex> lk(s->m);
+        if (s->holding) {
+            s->consumed++;
+            s->holding = false;
+            s->cv.notify_all();
         }
+        s->cv.wait(lk, [&] { return s->produced > s->consumed || s->finished; });
+        if (s->produced == s->consumed) return false;      // end of file (or a torn last record)
+        s->holding = true;
         s->next = 0;
-        w->i += (size_t)offs[n];
     }
-    *fh = s->hdrs[s->next];
+    const int b = (int)(s->consumed & 1);
+    *fh = s->hdrs[b][s->next];
     if (fh->u64s != 2) { dbde_end_file_walk(w); return false; }   // reference :416
-    memcpy(image, s->frames + px * s->next, px);
+    memcpy(image, s->frames[b] + px * s->next, px);
     s->next++;
     w->frames++;
     return true;
@@ -324,20 +396,17 @@ bool dbde_walk_a_file(dbde_file_walker *w, frame_header *fh, uint8_t *image) {
 
 void dbde_end_file_walk(dbde_file_walker *w) {
     if (!w) return;
-    if (w->fptr) fclose(w->fptr);
-    w->fptr = NULL;
+    WalkerSide *s = nullptr;
     if (w->buffer) {
-        {
-            std::lock_guard<std::mutex> lk(g_wmx);
-            auto it = g_wside.find(w->buffer);
-            if (it != g_wside.end()) {
-                if (it->second->registered) dbde_b200_host_unregister(w->buffer);
-                if (it->second->frames) dbde_b200_host_free(it->second->frames);
-                delete it->second;
-                g_wside.erase(it);
-            }
+        std::lock_guard<std::mutex> lk(g_wmx);
+        auto it = g_wside.find(w->buffer);
+        if (it != g_wside.end()) {
+            s = it->second;
+            g_wside.erase(it);
         }
-        free(w->buffer);
-        w->buffer = NULL;
     }
+    if (s) destroy_side(s);                                // joins the helper, closes the file, frees the buffers
+    else if (w->fptr) fclose(w->fptr);
+    w->fptr = NULL;
+    w->buffer = NULL;
 }
