@@ -531,6 +531,23 @@ class DropIn:
         self._unpack_8x8_partial(depth, minval, self._p(pay), 8, rm, dm, self._p(img))
         return img
 
+    def walk_open(self, path, frames_buffered=4):
+        """dbde_start_file_walk -> (walker struct, video header tuple) for stepwise use with walk_next / walk_close"""
+        vh = _VideoHeader()
+        w = self._start(path.encode(), frames_buffered, C.byref(vh))
+        return w, (vh.u64s, vh.height, vh.width, vh.frame_hz)
+
+    def walk_next(self, w):
+        """dbde_walk_a_file -> (frame header tuple, image) or None at the end"""
+        img = np.zeros((w.height, w.width), dtype=np.uint8)
+        fh = _FrameHeader()
+        if not self._walk(C.byref(w), C.byref(fh), self._p(img)):
+            return None
+        return (fh.u64s, fh.index, fh.elapsed_ns), img
+
+    def walk_close(self, w):
+        self._end(C.byref(w))
+
     def walk_file(self, path, frames_buffered=4):
         """-> (video header tuple, [(frame header tuple, image)])"""
         vh = _VideoHeader()

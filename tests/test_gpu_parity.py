@@ -603,6 +603,41 @@ def test_file_walker(dropin):
             os.unlink(path)
 
 
+def test_file_walkers_side_by_side_early_close_and_damaged_frame(dropin):
+    """the walker's helper thread: two files walked alternately, one closed long before its end (the helper is
+    mid-batch or waiting), a file whose 6th record is damaged (frames 0-4 come out, then the walk ends as at
+    dbde_util.cpp:416), and a file cut in the middle of a record"""
+    W, H, N = 200, 120, 23
+    wh = 25 * 15
+    fr = synth.gen_frames("mix", N, W, H)
+    stream, sizes = ORA.pack_frames(fr, 0)
+    hdr = ORA.pack_video_header(3, H, W, 30.0).tobytes()
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    with tempfile.TemporaryDirectory() as d:
+        good, bad, cut = (os.path.join(d, n) for n in ("good.dbde", "bad.dbde", "cut.dbde"))
+        open(good, "wb").write(hdr + stream.tobytes())
+        dmg = stream.copy(); dmg[int(offs[5]) + 28 + 2 * wh] ^= 1
+        open(bad, "wb").write(hdr + dmg.tobytes())
+        open(cut, "wb").write(hdr + stream[:int(offs[9]) + 100].tobytes())
+        a, vha = dropin.walk_open(good, 3)
+        b, vhb = dropin.walk_open(good, 5)
+        assert vha == vhb == (3, H, W, 30.0)
+        for i in range(N):
+            ra = dropin.walk_next(a)
+            assert ra[0] == (2, i, 0) and (ra[1] == fr[i]).all()
+            if i < 4:
+                rb = dropin.walk_next(b)
+                assert rb[0] == (2, i, 0) and (rb[1] == fr[i]).all()
+            if i == 4:
+                dropin.walk_close(b)                      # 19 frames early
+        assert dropin.walk_next(a) is None
+        dropin.walk_close(a)
+        vh, frames = dropin.walk_file(bad, 4)
+        assert len(frames) == 5 and all((img == fr[i]).all() for i, (_, img) in enumerate(frames))
+        vh, frames = dropin.walk_file(cut, 4)
+        assert len(frames) == 9 and all((img == fr[i]).all() for i, (_, img) in enumerate(frames))
+
+
 def test_the_references_own_test_program_passes_against_this_library():
     """dbde_util_test.cpp -- the reference's whole test main (example tiles incl. the
     three partial-tile cases, the 8x16 known-answer test in both directions, the 2536x2048 noise
