@@ -109,22 +109,22 @@ static size_t payload_align_delta(int W, int H) {
 // The reference's two compile-time variants.  Building this library with the same
 // macros makes them the defaults; dbde_b200_set_format_variants() switches them at run time.
 #ifdef DBDE_INVERT_ENDIAN
-static int g_invert_endian = 1;
+static std::atomic<int> g_invert_endian{1};
 #else
-static int g_invert_endian = 0;
+static std::atomic<int> g_invert_endian{0};
 #endif
 #ifdef DBDE_HZ_AS_INTEGER
-static int g_hz_as_integer = 1;
+static std::atomic<int> g_hz_as_integer{1};
 #else
-static int g_hz_as_integer = 0;
+static std::atomic<int> g_hz_as_integer{0};
 #endif
 extern "C" void dbde_b200_set_format_variants(int invert_endian, int hz_as_integer) {
-    g_invert_endian = invert_endian ? 1 : 0;
-    g_hz_as_integer = hz_as_integer ? 1 : 0;
+    g_invert_endian.store(invert_endian ? 1 : 0, std::memory_order_relaxed);
+    g_hz_as_integer.store(hz_as_integer ? 1 : 0, std::memory_order_relaxed);
 }
 extern "C" void dbde_b200_get_format_variants(int *invert_endian, int *hz_as_integer) {
-    if (invert_endian) *invert_endian = g_invert_endian;
-    if (hz_as_integer) *hz_as_integer = g_hz_as_integer;
+    if (invert_endian) *invert_endian = g_invert_endian.load(std::memory_order_relaxed);
+    if (hz_as_integer) *hz_as_integer = g_hz_as_integer.load(std::memory_order_relaxed);
 }
 
 // ------------------------------------------------------------------ lifetime
@@ -150,7 +150,7 @@ extern "C" int dbde_b200_create(int device, dbde_b200_ctx **out) {
     dbde_b200_ctx *c = new dbde_b200_ctx();
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
-    c->invert_endian = g_invert_endian;
+    c->invert_endian = g_invert_endian.load(std::memory_order_relaxed);
     if (const char *e = getenv("DBDE_B200_SLOTS")) {
         const int n = atoi(e);
         if (n >= 2 && n <= kMaxHostSlots) c->nslots = n;
