@@ -44,6 +44,20 @@ __device__ __forceinline__ void load_tile16(const uint16_t *frame, int W, int H,
         if (aligned && cols_valid == 8) {
             const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(row));
             px[4 * r] = v.x; px[4 * r + 1] = v.y; px[4 * r + 2] = v.z; px[4 * r + 3] = v.w;
+        } else if (cols_valid == 8) {
+            // a full row of an odd-width frame: 4-byte accesses (the row starts on an even or an odd pixel)
+            if (((uintptr_t)row & 3) == 0) {
+                const uint32_t *r32 = reinterpret_cast<const uint32_t *>(row);
+#pragma unroll
+                for (int j = 0; j < 4; j++) px[4 * r + j] = r32[j];
+            } else {
+                const uint32_t *r32 = reinterpret_cast<const uint32_t *>(row + 1);
+                const uint32_t a0 = row[0], w0 = r32[0], w1 = r32[1], w2 = r32[2], a7 = row[7];
+                px[4 * r] = a0 | (w0 << 16);
+                px[4 * r + 1] = __funnelshift_r(w0, w1, 16);
+                px[4 * r + 2] = __funnelshift_r(w1, w2, 16);
+                px[4 * r + 3] = (w2 >> 16) | (a7 << 16);
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -70,6 +84,19 @@ __device__ __forceinline__ void store_tile16(uint16_t *frame, int W, int H, int 
         uint16_t *row = frame + (size_t)(8 * ty + r) * W + 8 * tx;
         if (aligned && cols_valid == 8) {
             st_stream_v4u32(row, make_uint4(px[4 * r], px[4 * r + 1], px[4 * r + 2], px[4 * r + 3]));
+        } else if (cols_valid == 8) {
+            if (((uintptr_t)row & 3) == 0) {
+                uint32_t *r32 = reinterpret_cast<uint32_t *>(row);
+#pragma unroll
+                for (int j = 0; j < 4; j++) r32[j] = px[4 * r + j];
+            } else {
+                uint32_t *r32 = reinterpret_cast<uint32_t *>(row + 1);
+                row[0] = (uint16_t)px[4 * r];
+                r32[0] = __funnelshift_r(px[4 * r], px[4 * r + 1], 16);
+                r32[1] = __funnelshift_r(px[4 * r + 1], px[4 * r + 2], 16);
+                r32[2] = __funnelshift_r(px[4 * r + 2], px[4 * r + 3], 16);
+                row[7] = (uint16_t)(px[4 * r + 3] >> 16);
+            }
         } else {
 #pragma unroll
             for (int c = 0; c < 8; c++)
