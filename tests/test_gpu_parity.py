@@ -391,6 +391,22 @@ def test_dbde16_of_8_bit_content_is_the_8_bit_codec(codec):
         pa += int(sa[i])
 
 
+def test_dbde16_full_size_frames_across_staging_batches(codec):
+    """2048x2048 U16 (8 MiB per frame): 20 frames cross the host path's 128 MiB staging batch, 256 partitions per
+    frame exercise the per-frame look-back chains; 12-bit camera-like content + two full-range frames"""
+    W = H = 2048
+    rng = np.random.default_rng(12)
+    y, x = np.mgrid[0:H, 0:W]
+    base = (600 + x // 16 + y // 8).astype(np.uint16)
+    fr = np.stack([base + rng.integers(0, 32, (H, W), dtype=np.uint16) for _ in range(18)]
+                  + [rng.integers(0, 65536, (H, W), dtype=np.uint16) for _ in range(2)])
+    want, sizes = oracle.port16.pack_frames(fr, 1000)
+    got, offs = codec.encode16_host(fr, 1000)
+    assert int(offs[20]) == len(want) and (got == want).all()
+    dec, status, index = codec.decode16_host(got, offs[:20], W, H)
+    assert (status == 0).all() and index.tolist() == list(range(1000, 1020)) and (dec == fr).all()
+
+
 def test_dbde16_rejects_damaged_records_and_many_frames(codec):
     W, H, N = 136, 72, 40
     wh = 17 * 9
