@@ -510,6 +510,9 @@ __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecPa
 // 2x SLOWER (0.85 vs 0.43 ms per 1000 frames) -- ~90 instructions per image row on ONE warp that gets a
 // seventh of its scheduler; spread over the tile warps it would cost what the narrow stores cost now.
 constexpr int kStgStages = 2;                                    // input stages
+// One output image per CTA: 2 x 17 KiB in + 16.5 KiB out = 4 CTAs/SM.  Measured against two images (3 CTAs/SM):
+// +7-10 % on every 1001x1003 workload (mix 3.54 -> 3.81 TB/s) -- a fourth CTA hides more than a second image does.
+constexpr int kStgOut = 1;                                       // output images
 constexpr int kStgThreads = kTilesPerPart + 64;
 constexpr int kStgOutBytes = 64 * kTilesPerPart + 128;           // image of <= 16 KiB + the 16-byte shift, 128-byte multiple
 using StgSmem = DecSmemT<kStgStages>;
@@ -554,7 +557,7 @@ __device__ __forceinline__ void sts_row8(uint32_t addr, uint32_t a, uint32_t lo,
     }
 }
 
-__global__ void __launch_bounds__(kStgThreads, 3) dbde_decode_staged_kernel(const DecParams P) {
+__global__ void __launch_bounds__(kStgThreads, kStgOut == 1 ? 4 : 3) dbde_decode_staged_kernel(const DecParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     StgSmem &S = *reinterpret_cast<StgSmem *>(smem_raw);
     uint8_t *stages = smem_raw + ((sizeof(StgSmem) + 127) & ~127);
@@ -591,7 +594,7 @@ __global__ void __launch_bounds__(kStgThreads, 3) dbde_decode_staged_kernel(cons
             if (lane == 0) mbar_arrive(&S.empty[s]);
             if (c0.x < 0) break;
             if (c0.y) continue;
-            const int os = oi & 1;
+            const int os = oi % kStgOut;
             const int nbands = c0.w / g.w;
             const int rows = min(8 * nbands, g.H - 8 * y0);
             const uint32_t n = (uint32_t)rows * (uint32_t)g.W;
@@ -601,7 +604,7 @@ __global__ void __launch_bounds__(kStgThreads, 3) dbde_decode_staged_kernel(cons
             const uint32_t head = min((16u - a16) & 15u, n);                       // bytes before the first 16-byte boundary
             const uint32_t mid = (n - head) & ~15u;                                // the aligned interior
             const uint32_t tail = n - head - mid;
-            mbar_wait_sleepy(&S.outfull[os], (oi >> 1) & 1);
+            mbar_wait_sleepy(&S.outfull[os], (oi / kStgOut) & 1);
             if (lane == 0 && mid) tma_store_1d(g0 + head, img + head, mid);
             if (lane == 0) tma_store_commit();
             if (lane < 16) {
@@ -644,8 +647,8 @@ __global__ void __launch_bounds__(kStgThreads, 3) dbde_decode_staged_kernel(cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.empty[s]);       // payload is in registers: free the stage early
 
-            const int os = oi & 1;
-            if (oi >= 2) mbar_wait(&S.outempty[os], ((oi >> 1) - 1) & 1);
+            const int os = oi % kStgOut;
+            if (oi >= kStgOut) mbar_wait(&S.outempty[os], ((oi / kStgOut) - 1) & 1);
             // The image's global address, recomputed from the partition id: the producer walks the
             // partitions in the static order blockIdx.x + it * gridDim.x, so frame and band are
             // block-uniform here and the row alignments below are uniform values.
@@ -695,7 +698,7 @@ cudaError_t launch_decode_scan(const DecParams &P, cudaStream_t stream) {
 }
 
 static size_t stg_smem_bytes() {
-    return ((sizeof(StgSmem) + 127) & ~(size_t)127) + (size_t)kStgStages * kDecStageBytes + 2 * (size_t)kStgOutBytes;
+    return ((sizeof(StgSmem) + 127) & ~(size_t)127) + (size_t)kStgStages * kDecStageBytes + kStgOut * (size_t)kStgOutBytes;
 }
 
 template <typename Kern>
