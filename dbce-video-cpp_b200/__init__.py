@@ -32,7 +32,7 @@ C_SYMBOLS = [
     "dbde_b200_encode_device", "dbde_b200_decode_device", "dbde_b200_encode_host", "dbde_b200_decode_host",
     "dbde_b200_encode_host_sharded", "dbde_b200_decode_host_sharded",
     "dbde_b200_frame_record_bound16", "dbde_b200_slot_stride16", "dbde_b200_encode16_device", "dbde_b200_decode16_device",
-    "dbde_b200_encode16_host", "dbde_b200_decode16_host",
+    "dbde_b200_encode16_host", "dbde_b200_decode16_host", "dbde_b200_index_stream16",
     "dbde_b200_index_stream", "dbde_b200_validate_device", "dbde_b200_validate_host", "dbde_b200_set_chunk_frames", "dbde_b200_kernel_launches",
     "dbde_b200_set_format_variants", "dbde_b200_get_format_variants", "dbde_b200_set_invert_endian",
     "dbde_b200_writer_open", "dbde_b200_writer_append", "dbde_b200_writer_close",
@@ -99,6 +99,8 @@ def load():
                                                   C.c_void_p, C.c_size_t, C.c_void_p]
     lib.dbde_b200_decode_host_sharded.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
                                                   C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dbde_b200_index_stream16.restype = C.c_long
+    lib.dbde_b200_index_stream16.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_long]
     lib.dbde_b200_index_stream.restype = C.c_long
     lib.dbde_b200_index_stream.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_long]
     lib.dbde_b200_set_chunk_frames.argtypes = [C.c_void_p, C.c_int]

@@ -846,16 +846,16 @@ extern "C" int dbde_b200_decode_host_sharded(dbde_b200_ctx **ctxs, int nctx, con
 }
 
 // ------------------------------------------------------------------ host indexer
-extern "C" long dbde_b200_index_stream(const uint8_t *p, size_t bytes, int W, int H, uint64_t *offs,
-                                       long max_frames) {
+// minbytes: bytes per tile in the minimum plane (1: the reference's records, 2: DBDE16)
+static long index_stream_impl(const uint8_t *p, size_t bytes, int W, int H, uint64_t *offs, long max_frames, size_t minbytes) {
     if (!p || !offs || !dims_ok(W, H, 0)) return fail(DBDE_B200_E_INVALID, "index_stream: bad argument");
     const size_t wh = (size_t)((W + 7) / 8) * ((H + 7) / 8);
-    const size_t fixed = 32 + 2 * wh;
+    const size_t fixed = 32 + (1 + minbytes) * wh;
     size_t cur = 0;
     long n = 0;
     while (cur + fixed <= bytes && n < max_frames) {
         uint32_t n64;
-        memcpy(&n64, p + cur + 28 + 2 * wh, 4);
+        memcpy(&n64, p + cur + fixed - 4, 4);
         const size_t next = cur + fixed + 8 * (size_t)n64;
         if (next > bytes) break;
         offs[n++] = cur;
@@ -863,4 +863,10 @@ extern "C" long dbde_b200_index_stream(const uint8_t *p, size_t bytes, int W, in
     }
     offs[n] = cur;
     return n;
+}
+extern "C" long dbde_b200_index_stream(const uint8_t *p, size_t bytes, int W, int H, uint64_t *offs, long max_frames) {
+    return index_stream_impl(p, bytes, W, H, offs, max_frames, 1);
+}
+extern "C" long dbde_b200_index_stream16(const uint8_t *p, size_t bytes, int W, int H, uint64_t *offs, long max_frames) {
+    return index_stream_impl(p, bytes, W, H, offs, max_frames, 2);
 }

@@ -173,6 +173,9 @@ DBDE_B200_API int dbde_b200_decode16_device(dbde_b200_ctx *ctx, const uint8_t *s
 DBDE_B200_API int dbde_b200_encode16_host(dbde_b200_ctx *ctx, const uint16_t *frames_host, int W, int H,
                                           uint64_t first_index, int nframes, uint8_t *out_host, size_t out_capacity,
                                           uint64_t *frame_offsets_host);
+/* the indexer for DBDE16 streams: next = cur + 32 + 3wh + 8*n64 */
+DBDE_B200_API long dbde_b200_index_stream16(const uint8_t *stream_host, size_t stream_bytes, int W, int H,
+                                            uint64_t *frame_offsets, long max_frames);
 DBDE_B200_API int dbde_b200_decode16_host(dbde_b200_ctx *ctx, const uint8_t *stream_host, size_t stream_bytes,
                                           const uint64_t *frame_offsets_host, int W, int H, int nframes,
                                           uint16_t *frames_host, uint32_t *status_host, uint64_t *indices_host);

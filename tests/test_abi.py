@@ -113,3 +113,21 @@ def test_integration_example_builds_and_refuses_to_run_without_a_gpu(lib):
     import torch
     if not torch.cuda.is_available():
         assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+def test_indexers_are_pure_host_arithmetic(lib):
+    """dbde_b200_index_stream / _index_stream16: the pointer chase over n64 the reference's walker does
+    implicitly (dbde_util.cpp:301,327), on streams made by the oracle -- no GPU involved"""
+    import numpy as np
+    import oracle
+    import synth
+    W, H, N = 77, 45, 9
+    fr = synth.gen_frames("mix", N, W, H)
+    for stream, sizes, fn in ((oracle.best().pack_frames(fr, 0)) + (lib.dbde_b200_index_stream,),
+                              (oracle.port16.pack_frames(fr.astype(np.uint16) * 200, 0)) + (lib.dbde_b200_index_stream16,)):
+        offs = np.zeros(N + 5, dtype=np.uint64)
+        buf = np.concatenate([stream, stream[:40]])              # a torn tenth record must not be counted
+        n = fn(buf.ctypes.data, buf.nbytes, W, H, offs.ctypes.data, N + 4)
+        assert n == N and offs[:N + 1].tolist() == [0] + np.cumsum(sizes).tolist()
+        assert fn(buf.ctypes.data, buf.nbytes, W, H, offs.ctypes.data, 4) == 4      # max_frames is honoured
+        assert fn(buf.ctypes.data, 10, W, H, offs.ctypes.data, 4) == 0
