@@ -375,6 +375,21 @@ def test_dbde16_matches_its_oracle(codec, W, H):
     assert (status == 0).all() and index.tolist() == list(range(77, 82)) and (dec == fr).all()
 
 
+def test_dbde16_frozen_fixtures_on_the_gpu(codec):
+    """the committed DBDE16 fixtures (tests/golden/golden16.json) through the CUDA path"""
+    import importlib.util
+    import json
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden16", os.path.join(gdir, "make_golden16.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    for c in json.load(open(os.path.join(gdir, "golden16.json")))["cases"]:
+        fr = mg.frames16(c)
+        got, offs = codec.encode16_host(fr, 11)
+        assert np.diff(offs).astype(np.int64).tolist() == c["sizes"] and sha(got) == c["stream_sha256"], c
+        dec, status, _ = codec.decode16_host(got, offs[:c["N"]], c["W"], c["H"])
+        assert (status == 0).all() and (dec == fr).all()
+
+
 def test_dbde16_of_8_bit_content_is_the_8_bit_codec(codec):
     """the embedding that ties the extension to the reference: pixels < 256 -> the reference's depth plane
     and U64 words, minima widened to two bytes"""

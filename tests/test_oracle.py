@@ -2,6 +2,7 @@
 (tests/golden/golden.json, produced by the unmodified reference) and, when oracle/_ref is built,
 differentially against the reference itself."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -244,3 +245,22 @@ def test_dbde16_embeds_the_8_bit_codec_and_round_trips():
     assert o16.unpack_frame(bad, 8, 8)[1][0] == 0xFFFFFFFF
     bad = s.copy(); bad[24] = 17
     assert o16.unpack_frame(bad, 8, 8)[1][0] == 0xFFFFFFFF
+
+
+def test_dbde16_frozen_fixtures():
+    """tests/golden/golden16.json freezes the extension's bytes (made by tests/golden/make_golden16.py from the
+    oracle's definition when DBDE16 was introduced): the format cannot drift silently"""
+    import json
+    sys_path = os.path.join(os.path.dirname(__file__), "golden")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden16", os.path.join(sys_path, "make_golden16.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    gold = json.load(open(os.path.join(sys_path, "golden16.json")))
+    for c in gold["cases"]:
+        fr = mg.frames16(c)
+        assert hashlib.sha256(fr.tobytes()).hexdigest() == c["frames_sha256"]
+        stream, sizes = oracle.port16.pack_frames(fr, 11)
+        assert [int(x) for x in sizes] == c["sizes"]
+        assert hashlib.sha256(stream.tobytes()).hexdigest() == c["stream_sha256"]
+        if "stream_hex" in c:
+            assert stream.tobytes().hex() == c["stream_hex"]
