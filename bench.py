@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--e2e-frames", type=int, default=0, help="frames per GPU in the end-to-end leg (0 = all that can be pinned)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip BASELINE configs 3 and 4 (run device-resident after the headline)")
+    ap.add_argument("--extra-steps", type=int, default=10)
     ap.add_argument("--kind", default=KIND, choices=["micro", "mix", "low", "noise"])
     ap.add_argument("--width", type=int, default=W)
     ap.add_argument("--height", type=int, default=H)
@@ -171,6 +173,115 @@ def run_reference(a):
 
 
 # ------------------------------------------------------------------------------------------ our arm
+class DeviceLeg:
+    """One workload resident in HBM: frames, record slots, decoded frames.  encode()/decode() are the two
+    launches of a step; gate() is the parity check that precedes any timing."""
+
+    def __init__(self, torch, synth, codec, dev, kind, Ww, Hh, N, f0):
+        self.torch, self.codec, self.dev = torch, codec, dev
+        self.kind, self.W, self.H, self.N, self.f0 = kind, Ww, Hh, N, f0
+        self.px = Ww * Hh
+        self.wh = ((Ww + 7) // 8) * ((Hh + 7) // 8)
+        self.cap = codec.stream_bound(Ww, Hh, N)
+        self.stride = codec.slot_stride(Ww, Hh)
+        self.frames = torch.empty(N * self.px + 64, dtype=torch.uint8, device=dev)
+        self.stream_buf = torch.empty(self.cap + 64, dtype=torch.uint8, device=dev)
+        self.decoded = torch.empty(N * self.px + 64, dtype=torch.uint8, device=dev)
+        self.offs = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+        self.sizes = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+        self.status = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.delta = (16 - (32 + 2 * self.wh) % 16) % 16       # puts every frame's U64 words on 8/16-byte boundaries
+        self.out_ptr = self.stream_buf.data_ptr() + self.delta
+        self.cs = torch.cuda.current_stream().cuda_stream
+        synth.gen_frames_device(kind, N, Ww, Hh, self.frames.data_ptr(), seed=42, f0=f0, stream=self.cs)
+        torch.cuda.synchronize()
+
+    def encode(self):
+        self.codec.encode_device(self.frames.data_ptr(), self.W, self.H, self.f0, self.N, self.out_ptr, self.cap,
+                                 self.offs.data_ptr(), self.sizes.data_ptr(), self.cs)
+
+    def decode(self):
+        # the decoder reads each record from its slot (offs[i] = i * slot_stride)
+        self.codec.decode_device(self.out_ptr, self.cap, self.offs.data_ptr(), self.W, self.H, self.N,
+                                 self.decoded.data_ptr(), self.status.data_ptr(), None, self.cs)
+
+    def gate(self, threads):
+        """Parity before timing: decode(encode(x)) == x, and EVERY record byte-identical to what the
+        reference's dbde_pack_frame writes for the same frame (oracle/_ref when it is there, else the port
+        on a sample).  -> (total record bytes, algorithmic bytes per launch, description of the check)"""
+        torch, N, px, wh = self.torch, self.N, self.px, self.wh
+        self.encode()
+        torch.cuda.synchronize()
+        sizes = self.sizes[:N].cpu().numpy().astype(np.int64)
+        total = int(sizes.sum())
+        self.decode()
+        torch.cuda.synchronize()
+        assert int(self.status.abs().sum().item()) == 0, "decode rejected frames"
+        assert torch.equal(self.frames[:N * px], self.decoded[:N * px]), "decode(encode(x)) != x"
+        import oracle
+        slots = self.stream_buf[self.delta:self.delta + N * self.stride].view(N, self.stride)
+        frames = self.frames[:N * px].view(N, self.H, self.W)
+        step = max(1, min(N, (256 << 20) // max(px, 1)))
+        checked = 0
+        if oracle.ref is not None:
+            for a in range(0, N, step):
+                b = min(N, a + step)
+                fr = frames[a:b].cpu().numpy()
+                _, want, wsz = oracle.ref_encode_mt(fr, threads, 1)        # the reference writes index i - a
+                got = slots[a:b].cpu().numpy()
+                assert (wsz.astype(np.int64) == sizes[a:b]).all(), "record sizes differ from the reference"
+                for i in range(b - a):
+                    n = int(sizes[a + i])
+                    assert got[i, :4].tobytes() == want[i, :4].tobytes() and got[i, 12:n].tobytes() == want[i, 12:n].tobytes(), \
+                        "record %d differs from the reference" % (a + i)
+                    assert int(got[i, 4:12].view(np.uint64)[0]) == self.f0 + a + i, "frame index field"
+                checked += b - a
+            how = "all %d records byte-identical to the unmodified reference (oracle/_ref), round trip exact" % checked
+        else:
+            ns = min(N, 4)
+            want, wsz = oracle.port.pack_frames(frames[:ns].cpu().numpy(), self.f0)
+            got = np.concatenate([slots[i, :int(sizes[i])].cpu().numpy() for i in range(ns)])
+            assert np.array_equal(got, want), "records differ from the oracle port"
+            how = "first %d records byte-identical to the oracle port (oracle/_ref absent), round trip exact" % ns
+        n64_total = (total - N * (32 + 2 * wh)) // 8
+        alg = N * px + 2 * N * wh + 8 * n64_total            # per launch, same both directions (SURVEY 8d)
+        return total, alg, how
+
+    def timed(self, steps, warmup, barrier):
+        """`warmup` untimed steps, then EXACTLY `steps` timed ones (CUDA events on the launching stream)."""
+        torch = self.torch
+        for _ in range(warmup):
+            self.encode(); self.decode()
+        barrier()
+        l0 = self.codec.launches()
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        start.record()
+        for k in range(steps):
+            ev[k][0].record()
+            self.encode()
+            ev[k][1].record()
+            self.decode()
+            ev[k][2].record()
+        end.record()
+        barrier()
+        t1 = time.perf_counter()
+        return {"elapsed_ms": start.elapsed_time(end), "launches": self.codec.launches() - l0, "t_host": (t0, t1),
+                "enc_ms": float(np.mean([e[0].elapsed_time(e[1]) for e in ev])),
+                "dec_ms": float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))}
+
+    def free(self):
+        self.frames = self.stream_buf = self.decoded = None
+
+
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -190,71 +301,27 @@ def run_ours(a):
     codec = pkg.Codec(local)
     Ww, Hh, N = a.width, a.height, a.frames
     px = Ww * Hh
-    wh = ((Ww + 7) // 8) * ((Hh + 7) // 8)
-    f0 = rank * N                                    # this GPU's contiguous frame range
-
-    # ---- resident buffers (torch owns the device memory; the codec gets raw pointers)
-    cap = codec.stream_bound(Ww, Hh, N)
-    frames = torch.empty(N * px + 64, dtype=torch.uint8, device=dev)
-    stream_buf = torch.empty(cap + 64, dtype=torch.uint8, device=dev)
-    decoded = torch.empty(N * px + 64, dtype=torch.uint8, device=dev)
-    offs = torch.zeros(N + 1, dtype=torch.int64, device=dev)
-    sizes = torch.zeros(N + 1, dtype=torch.int64, device=dev)
-    status = torch.zeros(N, dtype=torch.int32, device=dev)
-    delta = (16 - (32 + 2 * wh) % 16) % 16           # puts every frame's U64 words on 8/16-byte boundaries
-    out_ptr = stream_buf.data_ptr() + delta
-    cs = torch.cuda.current_stream().cuda_stream
-    synth.gen_frames_device(a.kind, N, Ww, Hh, frames.data_ptr(), seed=42, f0=f0, stream=cs)
-    torch.cuda.synchronize()
-
-    def encode():
-        codec.encode_device(frames.data_ptr(), Ww, Hh, f0, N, out_ptr, cap, offs.data_ptr(), sizes.data_ptr(), cs)
-
-    def decode(total):
-        # the decoder reads each record from its slot (offs[i] = i * slot_stride)
-        codec.decode_device(out_ptr, cap, offs.data_ptr(), Ww, Hh, N, decoded.data_ptr(), status.data_ptr(), None, cs)
-
-    # ---- correctness gate before any timing: round trip + a sample against the oracle
-    encode()
-    torch.cuda.synchronize()
-    total = int(sizes[:N].sum().item())           # bytes of all records (what a file would hold)
-    decode(total)
-    torch.cuda.synchronize()
-    assert int(status.abs().sum().item()) == 0, "decode rejected frames"
-    assert torch.equal(frames[:N * px], decoded[:N * px]), "decode(encode(x)) != x"
-    n64_total = (total - N * (32 + 2 * wh)) // 8
-    alg_bytes = N * px + 2 * N * wh + 8 * n64_total   # per launch, same both directions
+    shard = importlib.import_module("dbce-video-cpp_b200.shard")
+    f0, f1 = shard.frame_range(rank, world, world * N)     # this GPU's contiguous frame range (weak scaling: N each)
+    assert f1 - f0 == N
+    host_threads = max(1, (os.cpu_count() or 1) // world)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- resident buffers (torch owns the device memory; the codec gets raw pointers), parity gate
+    leg = DeviceLeg(torch, synth, codec, dev, a.kind, Ww, Hh, N, f0)
+    total, alg_bytes, gate_how = leg.gate(host_threads)
+    frames, decoded, sizes, stream_buf = leg.frames, leg.decoded, leg.sizes, leg.stream_buf
+
     # ---- warm-up, then EXACTLY K timed steps
-    for _ in range(a.warmup):
-        encode(); decode(total)
-    barrier()
-    launches0 = codec.launches()
     sampler = ClockSampler(local) if rank == 0 else None
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(a.steps)]
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_host0 = time.perf_counter()
-    start.record()
-    for k in range(a.steps):
-        ev[k][0].record()
-        encode()
-        ev[k][1].record()
-        decode(total)
-        ev[k][2].record()
-    end.record()
-    barrier()
-    t_host1 = time.perf_counter()
-    elapsed_ms = start.elapsed_time(end)
-    launches = codec.launches() - launches0
-    clocks = sampler.stop(t_host0, t_host1) if sampler else None
-    enc_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
-    dec_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
-    t = torch.tensor([elapsed_ms, enc_ms, dec_ms], dtype=torch.float64, device=dev)
+    tm = leg.timed(a.steps, a.warmup, barrier)
+    clocks = sampler.stop(*tm["t_host"]) if sampler else None
+    launches, enc_ms, dec_ms = tm["launches"], tm["enc_ms"], tm["dec_ms"]
+    t = torch.tensor([tm["elapsed_ms"], enc_ms, dec_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms, enc_ms_max, dec_ms_max = [float(x) for x in t.tolist()]
@@ -266,14 +333,15 @@ def run_ours(a):
     # two contexts driven by two host threads (the C ABI's contract: one context per thread), so the
     # encoder's H2D of raw frames overlaps the decoder's D2H of raw frames on the full-duplex PCIe
     # link.  Step k decodes the stream step k-1 encoded (same bytes every step).  The strictly
-    # sequential figure (encode_host, then decode_host, one context) is reported next to it.
+    # sequential figure (encode_host, then decode_host, one context) is reported next to it, and so is
+    # the CEILING: the same bytes moved by plain cudaMemcpy with no codec, all ranks at once.
     e2e = None
     if not a.no_e2e:
         from concurrent.futures import ThreadPoolExecutor
         codec2 = pkg.Codec(local)
-        # pinned host memory: frames + decoded frames + two worst-case stream buffers ~ 4.1 x raw bytes.
-        # Use the whole N-frame batch when the box can pin it for every rank, else the largest prefix
-        # that fits in a third of MemAvailable (throughput is steady-state either way).
+        # pinned host memory: frames + decoded frames + two stream buffers.  Use the whole N-frame batch
+        # when the box can pin it for every rank, else the largest prefix that fits in a third of
+        # MemAvailable (throughput is steady-state either way).
         Ne = N
         try:
             avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0]
@@ -284,15 +352,45 @@ def run_ours(a):
         except Exception:
             pass
         N_full, N = N, Ne                              # the e2e leg below runs on the first Ne frames
-        cap = codec.stream_bound(Ww, Hh, N)
         total = int(sizes[:N].sum().item())
-        h_frames = codec.pinned(N * px)
-        h_streams = [codec.pinned(cap), codec.pinned(cap)]
-        h_dec = codec.pinned(N * px)
+        # the stream buffers are sized from the records' real bytes (known from the device leg) plus slack,
+        # not from the 66*wh worst case; ONE pinned arena per process, carved into the four buffers
+        cap = (total + total // 8 + (1 << 20) + 4095) // 4096 * 4096
+        fb = (N * px + 4095) // 4096 * 4096
+        arena = codec.pinned(2 * fb + 2 * cap)
+
+        class View:
+            def __init__(self, off, n):
+                self.ptr, self.array = arena.ptr + off, arena.array[off:off + n]
+
+        h_frames, h_dec = View(0, N * px), View(fb, N * px)
+        h_streams = [View(2 * fb, cap), View(2 * fb + cap, cap)]
         h_offs = [np.zeros(N + 1, dtype=np.uint64), np.zeros(N + 1, dtype=np.uint64)]
         h_status = np.zeros(N, dtype=np.uint32)
         torch.cuda.synchronize()
-        codec.lib.dbde_b200_memcpy_d2h(codec.h, h_frames.ptr, frames.data_ptr(), N * px)
+        lib = codec.lib
+        lib.dbde_b200_memcpy_d2h(codec.h, h_frames.ptr, frames.data_ptr(), N * px)
+
+        # ceiling: one step's bytes per direction (raw frames + records) as plain asynchronous copies on
+        # two streams, H2D || D2H, no codec -- what the link and the host side give this many ranks at once
+        pool = ThreadPoolExecutor(2)
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+        t_frames, t_dec = torch.from_numpy(h_frames.array), torch.from_numpy(h_dec.array)
+        t_s0, t_s1 = torch.from_numpy(h_streams[0].array[:total]), torch.from_numpy(h_streams[1].array[:total])
+        assert t_frames.is_pinned() and t_s1.is_pinned(), "arena is not page-locked"
+        dt_ceiling = 1e30
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(s_up):
+                decoded[:N * px].copy_(t_frames, non_blocking=True)
+                decoded[:total].copy_(t_s0, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                t_dec.copy_(frames[:N * px], non_blocking=True)
+                t_s1.copy_(stream_buf[:total], non_blocking=True)
+            s_up.synchronize(); s_dn.synchronize()
+            dt_ceiling = min(dt_ceiling, time.perf_counter() - t0)
+        del t_frames, t_dec, t_s0, t_s1
 
         def enc_host(k):
             codec.encode_host_raw(h_frames.ptr, Ww, Hh, f0, N, h_streams[k % 2].ptr, cap, h_offs[k % 2].ctypes.data)
@@ -312,7 +410,6 @@ def run_ours(a):
             enc_host(k); dec_host(k, codec)
         dt_seq = time.perf_counter() - t0
         # concurrent: encode(k) || decode(k-1)
-        pool = ThreadPoolExecutor(2)
         barrier()
         t0 = time.perf_counter()
         for k in range(a.e2e_steps):
@@ -322,22 +419,50 @@ def run_ours(a):
         dt = time.perf_counter() - t0
         pool.shutdown()
         assert not h_status.any() and np.array_equal(h_dec.array, h_frames.array), "e2e round trip differs"
-        te = torch.tensor([dt, dt_seq], dtype=torch.float64, device=dev)
+        te = torch.tensor([dt, dt_seq, dt_ceiling], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        dt, dt_seq = [float(x) for x in te.tolist()]
-        e2e = {"value": world * 2 * N * px * a.e2e_steps / dt / 1e9, "unit": UNIT,
+        dt, dt_seq, dt_ceiling = [float(x) for x in te.tolist()]
+        e2e_value = world * 2 * N * px * a.e2e_steps / dt / 1e9
+        ceiling = world * 2 * N * px / dt_ceiling / 1e9
+        e2e = {"value": e2e_value, "unit": UNIT,
                "h2d_bytes_per_step": int(N * px + total + 8 * N), "d2h_bytes_per_step": int(total + 8 * (N + 1) + N * px + 4 * N),
                "steps": a.e2e_steps, "ms_per_step": 1000 * dt / a.e2e_steps, "frames_per_gpu_per_step": int(N),
+               "ceiling": ceiling, "frac": e2e_value / ceiling,
+               "ceiling_how": "the same bytes per direction (raw frames + records) as four plain cudaMemcpyAsync copies on pinned memory, "
+                              "H2D || D2H on two streams, every rank at once, no codec; best of 3, max over ranks",
                "sequential": {"value": world * 2 * N * px * a.e2e_steps / dt_seq / 1e9, "ms_per_step": 1000 * dt_seq / a.e2e_steps},
                "path": "dbde_b200_encode_host || dbde_b200_decode_host on pinned host buffers: two contexts on two host "
                        "threads, each chunked through 3 device staging slots; step k decodes the stream of step k-1"}
-        for b in [h_frames, h_dec] + h_streams:
-            b.free()
+        h_frames = h_dec = h_streams = None
+        arena.free()
         codec2.close()
         N = N_full
-        cap = codec.stream_bound(Ww, Hh, N)
         total = int(sizes[:N].sum().item())
+
+    # ---- the other single-GPU BASELINE configs, device-resident, in the same run (N = 1 only)
+    peak, peak_src = hbm_peak()
+    extra = []
+    if world == 1 and not a.no_extra:
+        for name, kind, ew, eh, en in [("BASELINE config 3: odd-size 1001x1003 depth mix", "mix", 1001, 1003, 1000),
+                                       ("BASELINE config 4: 4096x4096 low entropy", "low", 4096, 4096, 300)]:
+            try:
+                xl = DeviceLeg(torch, synth, codec, dev, kind, ew, eh, en, 0)
+                xt, xalg, xhow = xl.gate(host_threads)
+                xm = xl.timed(a.extra_steps, 3, barrier)
+                eg, dg = xalg / (xm["enc_ms"] * 1e-3) / 1e9, xalg / (xm["dec_ms"] * 1e-3) / 1e9
+                extra.append({"workload": "%s ('%s' generator, %d frames per launch, %d steps)" % (name, kind, en, a.extra_steps),
+                              "width": ew, "height": eh, "frames": en, "generator": kind,
+                              "encode": {"ms": xm["enc_ms"], "GBps": eg, "frac": eg / peak, "fps": en / (xm["enc_ms"] * 1e-3)},
+                              "decode": {"ms": xm["dec_ms"], "GBps": dg, "frac": dg / peak, "fps": en / (xm["dec_ms"] * 1e-3)},
+                              "raw_pixel_GBps": 2 * en * ew * eh / (xm["elapsed_ms"] / a.extra_steps * 1e-3) / 1e9,
+                              "algorithmic_bytes_per_launch": int(xalg), "compressed_ratio": xt / float(en * ew * eh),
+                              "parity": xhow})
+                xl.free()
+                del xl
+                torch.cuda.empty_cache()
+            except Exception as ex:            # an extra config must never take the headline line down
+                extra.append({"workload": name, "error": repr(ex)})
 
     if rank != 0:
         if world > 1:
@@ -345,25 +470,23 @@ def run_ours(a):
         return 0
 
     # ---- roofline of the dominant kernel (algorithmic bytes / CUDA-event duration)
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     enc_gbs, dec_gbs = alg_bytes / (enc_ms * 1e-3) / 1e9, alg_bytes / (dec_ms * 1e-3) / 1e9
     dom = "encode" if enc_ms >= dec_ms else "decode"
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))      # ncu dram__bytes_read+write per launch, captured for ONE workload
             if tj.get("workload") == {"kind": a.kind, "width": Ww, "height": Hh, "frames": N}:
                 traffic = tj.get(dom, {}).get("dram_bytes_per_launch")
+                traffic_src = "profiles/roofline_traffic.json (ncu --set full capture of this workload, %s; not re-measured in this run)" \
+                              % tj.get("capture", "see profiles/README.md")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": "dbde_%s_kernel" % dom, "achieved": enc_gbs if dom == "encode" else dec_gbs,
                 "peak": peak, "unit": "GB/s", "frac": (enc_gbs if dom == "encode" else dec_gbs) / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(alg_bytes),
                 "encode": {"ms": enc_ms, "GBps": enc_gbs, "frac": enc_gbs / peak},
                 "decode": {"ms": dec_ms, "GBps": dec_gbs, "frac": dec_gbs / peak,
                            "note": "scan pre-pass + unpack kernel, timed together"}}
@@ -385,13 +508,14 @@ def run_ours(a):
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic", "config": workload_config(a, {"n_gpus": world}),
+            "dtype": "u8", "data": "synthetic", "config": workload_config(a),
             "encode_fps": world * N / (enc_ms_max * 1e-3), "decode_fps": world * N / (dec_ms_max * 1e-3),
             "encode_raw_GBps": world * N * px / (enc_ms_max * 1e-3) / 1e9,
             "decode_raw_GBps": world * N * px / (dec_ms_max * 1e-3) / 1e9,
-            "compressed_ratio": total / float(N * px), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "compressed_ratio": total / float(N * px), "parity_gate": gate_how, "clocks": clocks, "e2e": e2e,
+            "gpu_launches": int(launches),
             "gpu_launches_note": "per step: 1 encode kernel + 2 decode kernels (scan, unpack); memset excluded",
-            "roofline": roofline, "cpu_baseline": cpu}
+            "roofline": roofline, "cpu_baseline": cpu, "extra_configs": extra}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -49,13 +49,23 @@ struct HostSlot {
     int n = 0, first = 0;
 };
 
+// Scan scratch (encode: ticket + look-back descriptors; decode: word prefixes) belongs to the STREAM a
+// launch goes to: launches on one stream are ordered, launches on different streams are not, so two
+// chunks in flight on two staging streams must never share a ticket counter or a prefix table.
+constexpr int kMaxStreamScratch = 16;
+struct StreamScratch {
+    bool used = false;
+    cudaStream_t st = nullptr;
+    void *enc = nullptr, *dec = nullptr;
+    size_t enc_bytes = 0, dec_bytes = 0;
+    uint64_t last_use = 0;
+};
+
 struct dbde_b200_ctx {
     int device = 0;
     int num_sms = 0;
-    void *enc_scratch = nullptr;
-    size_t enc_scratch_bytes = 0;
-    void *dec_scratch = nullptr;
-    size_t dec_scratch_bytes = 0;
+    StreamScratch scratch[kMaxStreamScratch];
+    uint64_t scratch_clock = 0;
     HostSlot slots[kMaxHostSlots];
     int nslots = kDefaultHostSlots;   // staging slots in flight (DBDE_B200_SLOTS)
     int chunk_frames = 0;             // frames per chunk, 0 = auto (DBDE_B200_CHUNK_FRAMES)
@@ -183,8 +193,10 @@ extern "C" void dbde_b200_destroy(dbde_b200_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (auto &s : c->slots) free_slot(s);
-    if (c->enc_scratch) cudaFree(c->enc_scratch);
-    if (c->dec_scratch) cudaFree(c->dec_scratch);
+    for (auto &x : c->scratch) {
+        if (x.enc) cudaFree(x.enc);
+        if (x.dec) cudaFree(x.dec);
+    }
     delete c;
 }
 
@@ -273,6 +285,31 @@ static int grow(void **p, size_t *have, size_t need) {
     return 0;
 }
 
+// the scratch entry of `st`; when all entries are taken the least recently used one is recycled
+// (cudaFree waits for the device, so nothing in flight still reads it)
+static StreamScratch &scratch_for(dbde_b200_ctx *c, cudaStream_t st) {
+    StreamScratch *lru = nullptr;
+    for (auto &x : c->scratch)
+        if (x.used && x.st == st) {
+            x.last_use = ++c->scratch_clock;
+            return x;
+        }
+    for (auto &x : c->scratch) {
+        if (!x.used) { lru = &x; break; }
+        if (!lru || x.last_use < lru->last_use) lru = &x;
+    }
+    if (lru->used) {
+        cudaDeviceSynchronize();
+        if (lru->enc) cudaFree(lru->enc);
+        if (lru->dec) cudaFree(lru->dec);
+        *lru = StreamScratch();
+    }
+    lru->used = true;
+    lru->st = st;
+    lru->last_use = ++c->scratch_clock;
+    return *lru;
+}
+
 // ------------------------------------------------------------------ device-resident hot path
 extern "C" int dbde_b200_encode_device(dbde_b200_ctx *c, const uint8_t *frames_dev, int W, int H,
                                        uint64_t first_index, int nframes, uint8_t *out_dev, size_t out_capacity,
@@ -296,16 +333,17 @@ extern "C" int dbde_b200_encode_device(dbde_b200_ctx *c, const uint8_t *frames_d
     if (nparts >= 0xFFFFFFF0ull) return fail(DBDE_B200_E_INVALID, "encode_device: batch too large");
     // scratch: [ticket | pad to 128][desc: nparts u64], zeroed per launch
     const size_t sbytes = 128 + 8 * (size_t)nparts;
-    int rc = grow(&c->enc_scratch, &c->enc_scratch_bytes, sbytes);
+    StreamScratch &sc = scratch_for(c, st);
+    int rc = grow(&sc.enc, &sc.enc_bytes, sbytes);
     if (rc) return rc;
-    CK(cudaMemsetAsync(c->enc_scratch, 0, sbytes, st));
+    CK(cudaMemsetAsync(sc.enc, 0, sbytes, st));
     P.frames = frames_dev;
     P.out = out_dev;
     P.slot_stride = slot_stride;
     P.frame_offsets = frame_offsets_dev;
     P.frame_sizes = frame_sizes_dev;
-    P.ticket = (unsigned int *)c->enc_scratch;
-    P.desc = (uint64_t *)((uint8_t *)c->enc_scratch + 128);
+    P.ticket = (unsigned int *)sc.enc;
+    P.desc = (uint64_t *)((uint8_t *)sc.enc + 128);
     P.first_index = first_index;
     P.nframes = nframes;
     P.nparts = (unsigned)nparts;
@@ -331,7 +369,8 @@ static int decode_device_impl(dbde_b200_ctx *c, const uint8_t *stream_dev, size_
     const unsigned long long nparts = (unsigned long long)nframes * P.g.ppf;
     if (nparts >= 0xFFFFFFF0ull) return fail(DBDE_B200_E_INVALID, "decode_device: batch too large");
     const size_t sbytes = 4 * (size_t)nframes * ((size_t)P.g.ppf * kConsumerWarps + 1);
-    int rc = grow(&c->dec_scratch, &c->dec_scratch_bytes, sbytes);
+    StreamScratch &sc = scratch_for(c, st);
+    int rc = grow(&sc.dec, &sc.dec_bytes, sbytes);
     if (rc) return rc;
     P.stream = stream_dev;
     P.stream_bytes = stream_bytes;
@@ -339,7 +378,7 @@ static int decode_device_impl(dbde_b200_ctx *c, const uint8_t *stream_dev, size_
     P.frames = frames_dev;
     P.status = status_dev;
     P.indices = indices_dev;
-    P.wprefix = (uint32_t *)c->dec_scratch;
+    P.wprefix = (uint32_t *)sc.dec;
     P.nframes = nframes;
     P.nparts = (unsigned)nparts;
     P.flags = c->invert_endian ? kFlagInvertRows : 0u;
@@ -636,13 +675,14 @@ extern "C" int dbde_b200_encode16_device(dbde_b200_ctx *c, const uint16_t *frame
     const unsigned long long nparts = (unsigned long long)nframes * P.ppf;
     if (nparts >= 0xFFFFFFF0ull) return fail(DBDE_B200_E_INVALID, "encode16_device: batch too large");
     const size_t sbytes = 128 + 8 * (size_t)nparts;
-    int rc = grow(&c->enc_scratch, &c->enc_scratch_bytes, sbytes);
+    StreamScratch &sc = scratch_for(c, st);
+    int rc = grow(&sc.enc, &sc.enc_bytes, sbytes);
     if (rc) return rc;
-    CK(cudaMemsetAsync(c->enc_scratch, 0, sbytes, st));
+    CK(cudaMemsetAsync(sc.enc, 0, sbytes, st));
     P.frames = frames_dev; P.out = out_dev; P.slot_stride = slot_stride;
     P.frame_offsets = frame_offsets_dev; P.frame_sizes = frame_sizes_dev;
-    P.ticket = (unsigned int *)c->enc_scratch;
-    P.desc = (uint64_t *)((uint8_t *)c->enc_scratch + 128);
+    P.ticket = (unsigned int *)sc.enc;
+    P.desc = (uint64_t *)((uint8_t *)sc.enc + 128);
     P.first_index = first_index; P.nframes = nframes; P.nparts = (unsigned)nparts;
     P.aligned = (W % 8 == 0) && (((uintptr_t)frames_dev & 15) == 0);
     CK(launch_encode16(P, c->num_sms, st));
@@ -665,11 +705,12 @@ extern "C" int dbde_b200_decode16_device(dbde_b200_ctx *c, const uint8_t *stream
     const unsigned long long nparts = (unsigned long long)nframes * P.ppf;
     if (nparts >= 0xFFFFFFF0ull) return fail(DBDE_B200_E_INVALID, "decode16_device: batch too large");
     const size_t sbytes = 4 * (size_t)nframes * ((size_t)(P.wh + 31) / 32 + 1);
-    int rc = grow(&c->dec_scratch, &c->dec_scratch_bytes, sbytes);
+    StreamScratch &sc = scratch_for(c, st);
+    int rc = grow(&sc.dec, &sc.dec_bytes, sbytes);
     if (rc) return rc;
     P.stream = stream_dev; P.stream_bytes = stream_bytes; P.frame_offsets = frame_offsets_dev;
     P.frames = frames_dev; P.status = status_dev; P.indices = indices_dev;
-    P.wprefix = (uint32_t *)c->dec_scratch;
+    P.wprefix = (uint32_t *)sc.dec;
     P.nframes = nframes; P.nparts = (unsigned)nparts;
     P.aligned = (W % 8 == 0) && (((uintptr_t)frames_dev & 15) == 0);
     CK(launch_decode16_scan(P, st));

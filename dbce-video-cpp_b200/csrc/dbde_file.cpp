@@ -104,7 +104,16 @@ extern "C" int dbde_b200_writer_open(dbde_b200_ctx *ctx, const char *path, int W
     put32(hdr, 3);
     put64(hdr + 4, (uint64_t)H);
     put64(hdr + 12, (uint64_t)W);
-    memcpy(hdr + 20, &frame_hz, 8);
+    // the container follows the process-wide DBDE_HZ_AS_INTEGER variant exactly as the drop-in
+    // dbde_pack_video_header does (dbde_util.cpp:203-204): one library, one file format
+    int hz_int = 0;
+    dbde_b200_get_format_variants(nullptr, &hz_int);
+    if (hz_int) {
+        const uint64_t hz = (uint64_t)(long long)(frame_hz + 0.5);
+        memcpy(hdr + 20, &hz, 8);
+    } else {
+        memcpy(hdr + 20, &frame_hz, 8);
+    }
     if (fwrite(hdr, 1, 28, f) != 28) {
         fclose(f);
         return ffail(DBDE_B200_E_INVALID, "writer_open: cannot write the video header");
@@ -229,7 +238,17 @@ extern "C" int dbde_b200_reader_open(dbde_b200_ctx *ctx, const char *path, int b
     }
     if (W) *W = r->W;
     if (H) *H = r->H;
-    if (frame_hz) memcpy(frame_hz, hdr + 20, 8);
+    if (frame_hz) {
+        int hz_int = 0;
+        dbde_b200_get_format_variants(nullptr, &hz_int);       // dbde_util.cpp:352-353
+        if (hz_int) {
+            uint64_t hz;
+            memcpy(&hz, hdr + 20, 8);
+            *frame_hz = (double)hz;
+        } else {
+            memcpy(frame_hz, hdr + 20, 8);
+        }
+    }
     r->offs.resize((size_t)r->batch + 1);
     // prime: first half-buffer of bytes, synchronously, into the read-ahead half of buf[cur]
     r->pos = r->cap / 2;

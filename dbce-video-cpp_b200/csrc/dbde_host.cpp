@@ -6,6 +6,7 @@
 // buffers of frames per GPU batch and hands them out one per call.
 #pragma GCC visibility push(default)      // the sixteen reference entry points are the library's C++ surface
 #include "../../include/dbde_util.h"
+bool dbde_advance_file_buffer(dbde_file_walker &w);      // exported by the reference object, not in its header
 #pragma GCC visibility pop
 #include "../../include/dbde_b200.h"
 
@@ -109,6 +110,29 @@ video_header dbde_unpack_video_header(uint8_t **packed) {
     return vh;
 }
 
+// The checks dbde_unpack_image makes before it touches the image (dbde_util.cpp:295-303), made on the
+// host in the reference's order and reading no more than the reference reads: nb (4 bytes), then nm,
+// then n64 against the depth sum.  `blk` points at the image block (after the 20-byte frame header).
+// Returns false for a block the reference rejects -- and for a depth byte > 8, which this library
+// rejects (documented deviation) -- so a malformed or foreign buffer never reaches the GPU path.
+namespace {
+bool image_block_ok(const uint8_t *blk, size_t wh, size_t *n64_out) {
+    if (get32(blk) != (uint32_t)wh) return false;                   // nb != w*h  (:296)
+    const uint8_t *depth = blk + 4;
+    if (get32(blk + 4 + wh) != (uint32_t)wh) return false;          // nm != w*h  (:299)
+    const uint32_t n64 = get32(blk + 8 + 2 * wh);
+    uint64_t sum = 0;
+    uint32_t big = 0;
+    for (size_t i = 0; i < wh; i++) {
+        sum += depth[i];
+        big |= depth[i] > 8u;
+    }
+    if (sum != n64 || big) return false;                            // sum(depth) != n64  (:302-303)
+    *n64_out = n64;
+    return true;
+}
+}  // namespace
+
 // ---------------------------------------------------------------- frames (GPU)
 // reference dbde_util.cpp:190-196
 size_t dbde_pack_frame(uint64_t index, uint8_t *image, int W, int H, uint8_t *target) {
@@ -128,11 +152,12 @@ size_t dbde_pack_image(uint8_t *image, int W, int H, uint8_t *target) {
 frame_header dbde_unpack_frame(uint8_t **packed, int W, int H, uint8_t *image) {
     uint8_t *rec = *packed;
     frame_header fh = dbde_unpack_frame_header(packed);        // always advances 20 bytes
-    // the reference has no length argument: bound the record by what its own fields claim
+    // the reference has no length argument: validate in its order (:295-303), then bound the record by
+    // its own fields; a rejected block leaves the pointer after the header and the image untouched
     const size_t wh = (size_t)((W + 7) / 8) * ((H + 7) / 8);
-    const size_t n64 = get32(rec + 28 + 2 * wh);
-    if (n64 > 8 * wh) {                                        // cannot equal sum(depth <= 8): reject without
-        fh.u64s = (uint32_t)-1;                                // reading past what a legal record may occupy
+    size_t n64 = 0;
+    if (!image_block_ok(rec + 20, wh, &n64)) {
+        fh.u64s = (uint32_t)-1;
         return fh;
     }
     const size_t bytes = 32 + 2 * wh + 8 * n64;
@@ -156,8 +181,8 @@ frame_header dbde_unpack_frame(uint8_t **packed, int W, int H, uint8_t *image) {
 // reference dbde_util.cpp:291-328: returns bytes consumed, 0 on a malformed block
 size_t dbde_unpack_image(uint8_t *packed, int W, int H, uint8_t *image) {
     const size_t wh = (size_t)((W + 7) / 8) * ((H + 7) / 8);
-    const size_t n64 = get32(packed + 8 + 2 * wh);
-    if (n64 > 8 * wh) return 0;
+    size_t n64 = 0;
+    if (!image_block_ok(packed, wh, &n64)) return 0;           // :296,299,303 before anything else is read
     const size_t body = 12 + 2 * wh + 8 * n64;
     std::vector<uint8_t> rec(20 + body);
     frame_header fh = {2, 0, 0};
@@ -226,6 +251,11 @@ struct WalkerSide {
     uint8_t *frames[2] = {nullptr, nullptr};
     std::vector<frame_header> hdrs[2];
     size_t have[2] = {0, 0};
+    // the reference's bookkeeping for the caller's struct (dbde_util.h:42-43): where each record of the
+    // batch ended in the buffer (`i` after that frame) and how much of the buffer was good data (`n`)
+    std::vector<size_t> iafter[2];
+    size_t nat[2] = {0, 0};
+    bool io_error = false;              // fread failed (dbde_advance_file_buffer's `false`)
     // hand-off: batch k lives in slot k & 1; the helper may run at most two batches ahead of `consumed`
     std::mutex m;
     std::condition_variable cv;
@@ -254,7 +284,10 @@ bool refill(WalkerSide *s) {
     }
     if (!feof(s->f)) {
         s->n += fread(s->buffer + s->n, 1, s->N - s->n, s->f);
-        if (ferror(s->f)) return false;
+        if (ferror(s->f)) {
+            s->io_error = true;
+            return false;
+        }
     }
     return true;
 }
@@ -266,6 +299,7 @@ bool produce(WalkerSide *s, int b) {
     std::vector<uint64_t> offs(s->batch + 1);
     const long n = dbde_b200_index_stream(s->buffer + s->i, s->n - s->i, s->W, s->H, offs.data(), s->batch);
     if (n <= 0) return false;                              // end of file (or a torn last record)
+    s->nat[b] = s->n;
     std::vector<uint32_t> status(n);
     std::vector<uint64_t> index(n);
     int rc = dbde_b200_decode_host(ctx(), s->buffer + s->i, (size_t)offs[n], offs.data(), s->W, s->H, (int)n, s->frames[b],
@@ -276,6 +310,7 @@ bool produce(WalkerSide *s, int b) {
         uint8_t *p = s->buffer + s->i + offs[k];
         s->hdrs[b][k] = dbde_unpack_frame_header(&p);
         if (status[k] != 0) s->hdrs[b][k].u64s = (uint32_t)-1;
+        s->iafter[b][k] = s->i + (size_t)offs[k + 1];
         s->have[b]++;
         if (s->hdrs[b][k].u64s != 2) { more = false; break; }      // the reference stops at the first bad frame (:416)
     }
@@ -350,6 +385,7 @@ dbde_file_walker dbde_start_file_walk(const char *name, int frames_buffered, vid
             return w;
         }
         s->hdrs[b].resize(frames_buffered);
+        s->iafter[b].resize(frames_buffered);
     }
     // the file buffer is ours from malloc to free: page-lock it so the records go to the GPU by DMA
     s->registered = dbde_b200_host_register(s->buffer, N) == 0;
@@ -389,9 +425,25 @@ bool dbde_walk_a_file(dbde_file_walker *w, frame_header *fh, uint8_t *image) {
     *fh = s->hdrs[b][s->next];
     if (fh->u64s != 2) { dbde_end_file_walk(w); return false; }   // reference :416
     memcpy(image, s->frames[b] + px * s->next, px);
+    // mirror the reference's bookkeeping (:421): `i` just after the record handed out, `n` the good data
+    // of the buffer it was read from; `frames` stays untouched, as in the reference
+    w->i = s->iafter[b][s->next];
+    w->n = s->nat[b];
     s->next++;
-    w->frames++;
     return true;
+}
+
+// reference dbde_util.cpp:394-406 (exported by the reference object although dbde_util.h does not
+// declare it): "make sure there is always plenty of buffer past the current index"; false only when
+// reading the file failed.  Here the helper thread tops the buffer up on its own, so the call waits
+// until the next batch is ready (or the file has ended) and reports the helper's read status.
+bool dbde_advance_file_buffer(dbde_file_walker &w) {
+    if (!w.fptr) return false;
+    WalkerSide *s = side_of(&w);
+    if (!s) return false;
+    std::unique_lock<std::mutex> lk(s->m);
+    s->cv.wait(lk, [&] { return s->produced > s->consumed || s->finished; });
+    return !s->io_error;
 }
 
 void dbde_end_file_walk(dbde_file_walker *w) {

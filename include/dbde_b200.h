@@ -88,7 +88,11 @@ DBDE_B200_API int dbde_b200_memcpy_d2h(dbde_b200_ctx *ctx, void *dst_host, const
  * frame_sizes_dev[i] the record's size (nframes entries each).  frames_dev: nframes*W*H bytes,
  * tightly packed rows (stride = W), as the reference's `image` argument.  Asynchronous on
  * `stream` (a cudaStream_t, NULL = default).  out_capacity must be >= nframes * slot_stride.
- * Fastest when (out_dev + 32 + 2*wh) is 16-byte aligned (U64 words land on 16-byte boundaries). */
+ * Fastest when (out_dev + 32 + 2*wh) is 16-byte aligned (U64 words land on 16-byte boundaries).
+ * Streams: the scan scratch a launch needs (ticket + look-back descriptors here, word prefixes in
+ * decode_device) is kept PER STREAM inside the context, so calls queued on different streams of one
+ * context may overlap on the device; calls on one stream are ordered by the stream.  The context
+ * itself is still driven by one host thread at a time. */
 DBDE_B200_API int dbde_b200_encode_device(dbde_b200_ctx *ctx, const uint8_t *frames_dev, int W, int H,
                                           uint64_t first_index, int nframes, uint8_t *out_dev,
                                           size_t out_capacity, size_t slot_stride, uint64_t *frame_offsets_dev,

@@ -131,3 +131,59 @@ def test_indexers_are_pure_host_arithmetic(lib):
         assert n == N and offs[:N + 1].tolist() == [0] + np.cumsum(sizes).tolist()
         assert fn(buf.ctypes.data, buf.nbytes, W, H, offs.ctypes.data, 4) == 4      # max_frames is honoured
         assert fn(buf.ctypes.data, 10, W, H, offs.ctypes.data, 4) == 0
+
+
+def test_library_exports_everything_the_reference_object_exports(lib):
+    """nm of libdbde_b200.so must contain every function symbol of the reference's dbde_util.o -- including
+    dbde_advance_file_buffer (dbde_util.cpp:394), which the reference exports without declaring it in
+    dbde_util.h -- so anything that links against the reference object links against this library."""
+    import subprocess
+    ref_o = os.path.join(ROOT, "oracle", "_ref", "dbde_util.o")
+    if os.path.exists(ref_o):
+        out = subprocess.run(["nm", "--defined-only", ref_o], capture_output=True, text=True, check=True).stdout
+        want = {l.split()[2] for l in out.splitlines() if len(l.split()) == 3 and l.split()[1] == "T"}
+        assert len(want) == 16, want
+    else:                                   # the GPU box: the reference object is not there, its symbol list is
+        want = set(pkg.CXX_SYMBOLS.values()) | {"_Z24dbde_advance_file_bufferR16dbde_file_walker"}
+    out = subprocess.run(["nm", "-D", "--defined-only", pkg.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    have = {l.split()[2] for l in out.splitlines() if len(l.split()) == 3}
+    assert want <= have, want - have
+
+
+_GUARD_PAGE_PROBE = r"""
+import ctypes as C, importlib, mmap, sys
+sys.path.insert(0, %r)
+pkg = importlib.import_module("dbce-video-cpp_b200")
+d = pkg.DropIn()
+libc = C.CDLL(None, use_errno=True)
+page = mmap.PAGESIZE
+m = mmap.mmap(-1, 2 * page)
+base = C.addressof(C.c_char.from_buffer(m))
+assert libc.mprotect(C.c_void_p(base + page), C.c_size_t(page), 0) == 0       # the second page faults on any access
+W = H = 64; wh = 64
+# (1) frame record: 20-byte header + nb, with nb wrong, ending exactly at the guard page
+rec = base + page - 24
+C.memmove(rec, (2).to_bytes(4, "little") + (7).to_bytes(8, "little") + bytes(8) + (wh + 1).to_bytes(4, "little"), 24)
+img = (C.c_uint8 * (W * H))(*([0xCD] * (W * H)))
+p = C.cast(rec, C.POINTER(C.c_uint8))
+fh = d._unpack_frame(C.byref(p), W, H, img)
+assert fh.u64s == 0xFFFFFFFF and fh.index == 7 and C.addressof(p.contents) == rec + 20
+# (2) image block: nb right, nm wrong, ending at the guard page
+blk = base + page - (8 + wh)
+C.memmove(blk, wh.to_bytes(4, "little") + bytes([3] * wh) + (wh - 1).to_bytes(4, "little"), 8 + wh)
+assert d._unpack_image(C.cast(blk, C.POINTER(C.c_uint8)), W, H, img) == 0
+assert bytes(img) == bytes([0xCD] * (W * H))
+print("ok")
+"""
+
+
+def test_malformed_blocks_are_rejected_without_reading_past_what_the_reference_reads(lib):
+    """dbde_unpack_image returns 0 right after reading nb when nb != w*h, and after nm when nm != w*h
+    (dbde_util.cpp:295-299): the drop-in must not touch a byte beyond those fields either.  The fields sit
+    at the very end of a mapped page followed by a PROT_NONE page; an over-read is a segfault.  Host code
+    only (the check precedes any GPU work), so this runs without a GPU; in a subprocess because the failure
+    mode is a crash."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, "-c", _GUARD_PAGE_PROBE % ROOT], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", (r.returncode, r.stdout[-500:], r.stderr[-1500:])

@@ -863,3 +863,91 @@ def test_decoder_and_encoder_never_write_outside_their_buffers(codec, W, H, N):
     finally:
         for p in (d_fr, d_out, d_dec, d_off, d_sz, d_st):
             codec.device_free(p)
+
+
+def test_sharded_host_api_across_all_visible_devices():
+    """SURVEY 8e on real hardware: one context per visible GPU, a batch cut into many chunk ranges dealt
+    round-robin over the DEVICES; the whole stream must hash like the reference's, decode must return the
+    source frames.  Skipped on a one-GPU box (test_sharded_* then put all contexts on device 0)."""
+    ndev = pkg.load().dbde_b200_device_count()
+    if ndev < 2:
+        pytest.skip("one visible GPU")
+    group = [pkg.Codec(i) for i in range(ndev)]
+    try:
+        for kind, W, H, n, chunk in [("micro", 1024, 512, 16 * ndev + 5, 4), ("mix", 1001, 1003, 6 * ndev + 1, 2),
+                                     ("low", 4096, 256, 3 * ndev, 1)]:
+            fr = synth.gen_frames(kind, n, W, H)
+            want, sizes = ORA.pack_frames(fr, 9000)
+            group[0].set_chunk_frames(chunk)
+            try:
+                stream, offs = pkg.encode_host_sharded(group, fr, 9000)
+            finally:
+                group[0].set_chunk_frames(0)
+            assert len(stream) == len(want) and sha(stream) == sha(want), (kind, ndev)
+            assert offs.tolist() == [0] + np.cumsum(sizes).tolist()
+            dec, status, index = pkg.decode_host_sharded(group, stream, offs[:-1], W, H)
+            assert (status == 0).all() and index.tolist() == list(range(9000, 9000 + n)) and sha(dec) == sha(fr)
+    finally:
+        for c in group:
+            c.close()
+
+
+def test_walker_struct_bookkeeping_mirrors_the_reference(dropin):
+    """dbde_util.h:40-47: after each dbde_walk_a_file the reference leaves `i` just past the record it
+    handed out and `n` at the end of the buffer's good data, never touches `frames`, and exports
+    dbde_advance_file_buffer (dbde_util.cpp:394-406: false only when reading the file failed)."""
+    import ctypes as C
+    W, H, N = 136, 72, 9
+    fr = synth.gen_frames("mix", N, W, H)
+    stream, sizes = ORA.pack_frames(fr, 0)
+    ends = np.cumsum(sizes).tolist()
+    adv = getattr(dropin.lib, "_Z24dbde_advance_file_bufferR16dbde_file_walker")
+    adv.restype = C.c_bool
+    with tempfile.NamedTemporaryFile(suffix=".dbde", delete=False) as f:
+        f.write(ORA.pack_video_header(3, H, W, 30.0).tobytes())
+        f.write(stream.tobytes())
+        path = f.name
+    try:
+        w, vh = dropin.walk_open(path, N + 3)            # the whole file fits in one buffer: i == record ends
+        assert adv(C.byref(w)) is True
+        for k in range(N):
+            hdr, img = dropin.walk_next(w)
+            assert hdr == (2, k, 0) and (img == fr[k]).all()
+            assert w.i == ends[k] and w.n == len(stream) and w.i <= w.n <= w.N and w.frames == 0
+        assert dropin.walk_next(w) is None
+        dropin.walk_close(w)
+        w, vh = dropin.walk_open(path, 2)                # small buffer: the invariants still hold
+        seen = 0
+        while True:
+            r = dropin.walk_next(w)
+            if r is None:
+                break
+            assert (r[1] == fr[seen]).all() and 0 < w.i <= w.n <= w.N and w.frames == 0
+            seen += 1
+        assert seen == N
+        dropin.walk_close(w)
+        assert adv(C.byref(w)) is False                  # a closed walker
+    finally:
+        os.unlink(path)
+
+
+def test_file_api_follows_the_hz_as_integer_variant(codec, dropin):
+    """one library, one container: a file written by dbde_b200_writer_* is read by the drop-in walker and
+    by dbde_b200_reader_* under both settings of DBDE_HZ_AS_INTEGER (dbde_util.cpp:203-204,352-353), and
+    its header bytes are the reference's (the variant build of the reference for the integer form)."""
+    fr = synth.gen_frames("micro", 5, 200, 96)
+    for hz_int, ora in ((False, ORA), (True, oracle.best_variants())):
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, "v.dbde")
+            try:
+                pkg.set_format_variants(False, hz_int)
+                pkg.write_file(codec, path, fr, hz=29.97, first_index=3, batch=2)
+                head = np.frombuffer(open(path, "rb").read(28), dtype=np.uint8)
+                assert (head == ora.pack_video_header(3, 96, 200, 29.97)).all(), hz_int
+                vh, frames = dropin.walk_file(path, 3)
+                assert vh == (3, 96, 200, 30.0 if hz_int else 29.97) and len(frames) == 5
+                assert all((img == fr[i]).all() and hdr == (2, 3 + i, 0) for i, (hdr, img) in enumerate(frames))
+                (W, H, hz), got, idx, st = pkg.read_file(codec, path, batch=2)
+                assert (W, H, hz) == (200, 96, 30.0 if hz_int else 29.97) and (got == fr).all() and (st == 0).all()
+            finally:
+                pkg.set_format_variants(False, False)
