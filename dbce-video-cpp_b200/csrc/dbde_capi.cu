@@ -5,7 +5,10 @@
 #include "dbde_kernels.h"
 
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
+#include <deque>
+#include <mutex>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -44,6 +47,13 @@ struct HostSlot {
     uint64_t *d_index = nullptr;
     uint64_t *h_off = nullptr;   // pinned
     uint64_t *h_size = nullptr;  // pinned
+    uint32_t *h_status = nullptr;   // pinned mirrors of d_status / d_index (decode)
+    uint64_t *h_index = nullptr;
+    // pageable caller buffers (the reference's callers pass malloc'd memory, dbde_util.h:24-35): pinned
+    // bounce buffers the bytes are relayed through in pieces, by parallel memcpy overlapped with the DMA
+    uint8_t *h_in = nullptr, *h_out = nullptr;
+    size_t cap_hin = 0, cap_hout = 0;
+    cudaEvent_t pev[16] = {};    // one per piece of a relayed D2H copy
     size_t cap_a = 0, cap_b = 0, cap_c = 0;
     int cap_n = 0;
     int n = 0, first = 0;
@@ -183,6 +193,12 @@ static void free_slot(HostSlot &s) {
     if (s.d_status) cudaFree(s.d_status);
     if (s.d_index) cudaFree(s.d_index);
     if (s.h_off) cudaFreeHost(s.h_off);
+    if (s.h_status) cudaFreeHost(s.h_status);
+    if (s.h_index) cudaFreeHost(s.h_index);
+    if (s.h_in) cudaFreeHost(s.h_in);
+    if (s.h_out) cudaFreeHost(s.h_out);
+    for (auto &e : s.pev)
+        if (e) cudaEventDestroy(e);
     if (s.ev) cudaEventDestroy(s.ev);
     if (s.st) cudaStreamDestroy(s.st);
     s = HostSlot();
@@ -408,6 +424,169 @@ extern "C" int dbde_b200_validate_device(dbde_b200_ctx *c, const uint8_t *stream
                               indices_dev, stream, true);
 }
 
+// ------------------------------------------------------------------ pageable host memory
+// cudaMemcpyAsync on pageable memory goes through the driver's own staging at ~15 GB/s and blocks the
+// caller; a single host thread's memcpy is no faster (~14 GB/s).  The library therefore relays pageable
+// buffers itself: a small process-wide pool of copy threads moves the bytes between the caller's memory
+// and a pinned bounce buffer in pieces, and each piece's DMA is queued as soon as the piece is there (H2D)
+// / each piece is copied out as soon as its DMA has landed (D2H).  Callers that wait for their pieces
+// execute queued pieces themselves, so many calling threads (one context each) share the pool's work
+// instead of queueing behind it.  Nothing is page-locked behind the caller's back.
+namespace {
+class CopyPool {
+  public:
+    struct Job {
+        uint8_t *dst;
+        const uint8_t *src;
+        size_t n;
+        std::atomic<int> *pending;
+    };
+    static CopyPool &get() {
+        static CopyPool p;
+        return p;
+    }
+    void submit(uint8_t *dst, const uint8_t *src, size_t n, std::atomic<int> *pending) {
+        pending->fetch_add(1, std::memory_order_relaxed);
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            q_.push_back(Job{dst, src, n, pending});
+        }
+        queued_.fetch_add(1, std::memory_order_release);
+        cv_.notify_one();
+    }
+    bool run_one() {
+        if (queued_.load(std::memory_order_acquire) <= 0) return false;
+        Job j;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            if (q_.empty()) return false;
+            j = q_.front();
+            q_.pop_front();
+        }
+        queued_.fetch_sub(1, std::memory_order_relaxed);
+        memcpy(j.dst, j.src, j.n);
+        j.pending->fetch_sub(1, std::memory_order_release);
+        return true;
+    }
+    // wait until the jobs counted by `pending` are done, copying queued pieces (anyone's) meanwhile
+    void wait(std::atomic<int> &pending) {
+        while (pending.load(std::memory_order_acquire) > 0)
+            if (!run_one()) __builtin_ia32_pause();
+    }
+
+  private:
+    CopyPool() {
+        int n = (int)std::thread::hardware_concurrency() / 2;
+        if (n > 6) n = 6;
+        if (const char *e = getenv("DBDE_B200_COPY_THREADS")) n = atoi(e);
+        if (n < 0) n = 0;
+        for (int i = 0; i < n; i++) th_.emplace_back([this] { work(); });
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    void work() {
+        for (;;) {
+            // a caller in a loop finds the threads still spinning; an idle process finds them asleep
+            bool did = false;
+            for (int spin = 0; spin < 4000; spin++) {
+                if (run_one()) { did = true; break; }
+                __builtin_ia32_pause();
+            }
+            if (did) continue;
+            std::unique_lock<std::mutex> lk(m_);
+            cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+            if (stop_) return;
+        }
+    }
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<Job> q_;
+    std::atomic<int> queued_{0};
+    std::vector<std::thread> th_;
+    bool stop_ = false;
+};
+
+bool is_pageable(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+constexpr int kRelayPieces = 16;
+size_t relay_piece(size_t n) {
+    size_t piece = (n + kRelayPieces - 1) / kRelayPieces;
+    if (piece < (256u << 10)) piece = 256u << 10;
+    return (piece + 4095) & ~(size_t)4095;
+}
+}  // namespace
+
+static int ensure_bounce(HostSlot &s, size_t need_in, size_t need_out) {
+    if (need_in && s.cap_hin < need_in) {
+        if (s.h_in) CK(cudaFreeHost(s.h_in));
+        s.h_in = nullptr;
+        CK(cudaHostAlloc(&s.h_in, need_in, cudaHostAllocDefault));
+        s.cap_hin = need_in;
+    }
+    if (need_out && s.cap_hout < need_out) {
+        if (s.h_out) CK(cudaFreeHost(s.h_out));
+        s.h_out = nullptr;
+        CK(cudaHostAlloc(&s.h_out, need_out, cudaHostAllocDefault));
+        s.cap_hout = need_out;
+    }
+    if (need_out && !s.pev[0])
+        for (auto &e : s.pev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return 0;
+}
+
+// pageable src -> device, through the slot's pinned h_in (at offset hoff), queued on the slot's stream.
+// Returns when every piece's DMA is queued; the bounce bytes stay valid until the stream has passed them.
+static int relay_h2d(HostSlot &s, uint8_t *d_dst, const uint8_t *src, size_t n, size_t hoff) {
+    CopyPool &pool = CopyPool::get();
+    const size_t piece = relay_piece(n);
+    std::atomic<int> pend[kRelayPieces];
+    int np = 0;
+    for (size_t o = 0; o < n; o += piece, np++) {
+        pend[np].store(0, std::memory_order_relaxed);
+        pool.submit(s.h_in + hoff + o, src + o, n - o < piece ? n - o : piece, &pend[np]);
+    }
+    int j = 0;
+    for (size_t o = 0; o < n; o += piece, j++) {
+        pool.wait(pend[j]);
+        CK(cudaMemcpyAsync(d_dst + o, s.h_in + hoff + o, n - o < piece ? n - o : piece, cudaMemcpyHostToDevice, s.st));
+    }
+    return 0;
+}
+
+// device -> pageable dst, through the slot's pinned h_out (at offset hoff).  Synchronous: the bytes are in
+// dst on return.  Pieces are copied out by the pool while later pieces are still crossing PCIe.
+static int relay_d2h(HostSlot &s, uint8_t *dst, const uint8_t *d_src, size_t n, size_t hoff) {
+    if (!n) return 0;
+    CopyPool &pool = CopyPool::get();
+    const size_t piece = relay_piece(n);
+    int np = 0;
+    for (size_t o = 0; o < n; o += piece, np++) {
+        CK(cudaMemcpyAsync(s.h_out + hoff + o, d_src + o, n - o < piece ? n - o : piece, cudaMemcpyDeviceToHost, s.st));
+        CK(cudaEventRecord(s.pev[np], s.st));
+    }
+    std::atomic<int> pend{0};
+    int j = 0;
+    for (size_t o = 0; o < n; o += piece, j++) {
+        CK(cudaEventSynchronize(s.pev[j]));
+        pool.submit(dst + o, s.h_out + hoff + o, n - o < piece ? n - o : piece, &pend);
+    }
+    pool.wait(pend);
+    return 0;
+}
+
 // ------------------------------------------------------------------ host-buffer hot path
 static int default_chunk(const dbde_b200_ctx *c, int W, int H, int nframes) {
     int n = c->chunk_frames;
@@ -448,13 +627,18 @@ static int ensure_slot(dbde_b200_ctx *c, HostSlot &s, size_t need_a, size_t need
         if (s.d_status) CK(cudaFree(s.d_status));
         if (s.d_index) CK(cudaFree(s.d_index));
         if (s.h_off) CK(cudaFreeHost(s.h_off));
+        if (s.h_status) CK(cudaFreeHost(s.h_status));
+        if (s.h_index) CK(cudaFreeHost(s.h_index));
         s.d_off = nullptr; s.d_size = nullptr; s.h_size = nullptr; s.d_status = nullptr; s.d_index = nullptr; s.h_off = nullptr;
+        s.h_status = nullptr; s.h_index = nullptr;
         CK(cudaMalloc(&s.d_off, 8 * (size_t)(n + 1)));
         CK(cudaMalloc(&s.d_size, 8 * (size_t)(n + 1)));
         CK(cudaHostAlloc(&s.h_size, 8 * (size_t)(n + 1), cudaHostAllocDefault));
         CK(cudaMalloc(&s.d_status, 4 * (size_t)n));
         CK(cudaMalloc(&s.d_index, 8 * (size_t)n));
         CK(cudaHostAlloc(&s.h_off, 8 * (size_t)(n + 1), cudaHostAllocDefault));
+        CK(cudaHostAlloc(&s.h_status, 4 * (size_t)(n + 1), cudaHostAllocDefault));
+        CK(cudaHostAlloc(&s.h_index, 8 * (size_t)(n + 1), cudaHostAllocDefault));
         s.cap_n = n;
     }
     return 0;
@@ -480,13 +664,17 @@ static int encode_host_worker(dbde_b200_ctx *c, const uint8_t *frames_host, int 
     const int nchunks = (nframes + chunk - 1) / chunk;
     const int mine = nchunks > my ? (nchunks - my + nworkers - 1) / nworkers : 0;
     const int ns = mine < c->nslots ? mine : c->nslots;            // a one-frame call sets up one slot
+    // pageable caller memory is relayed through pinned bounce buffers (see CopyPool)
+    const bool in_pageable = is_pageable(frames_host), out_pageable = is_pageable(out_host);
     for (int i = 0; i < ns; i++) {
-        int rc = ensure_slot(c, c->slots[i], need_a, need_b, need_b, chunk);
+        int rc = ensure_slot(c, c->slots[i], need_a, need_b, chunk > 1 ? need_b : 0, chunk);
+        if (!rc) rc = ensure_bounce(c->slots[i], in_pageable ? px * chunk : 0, out_pageable ? need_b : 0);
         if (rc) return rc;
     }
     const size_t stride = dbde_b200_slot_stride(W, H);
     // finish(): wait for a chunk's kernels, learn the record sizes, claim the chunk's place in the
-    // stream, and queue ONE D2H copy of its records -- already laid back to back on the device.
+    // stream, and queue ONE D2H copy of its records -- already laid back to back on the device
+    // (a one-frame chunk's record is contiguous in its slot as it is: no compaction pass).
     auto finish = [&](int li) -> int {
         HostSlot &s = c->slots[li % ns];
         const int ci = my + li * nworkers;
@@ -506,7 +694,9 @@ static int encode_host_worker(dbde_b200_ctx *c, const uint8_t *frames_host, int 
             frame_offsets_host[s.first + i] = run;
             run += s.h_size[i];
         }
-        CK(cudaMemcpyAsync(out_host + pos, s.d_c, total, cudaMemcpyDeviceToHost, s.st));
+        const uint8_t *d_rec = chunk > 1 ? s.d_c : s.d_b + delta;
+        if (out_pageable) return relay_d2h(s, out_host + pos, d_rec, total, 0);
+        CK(cudaMemcpyAsync(out_host + pos, d_rec, total, cudaMemcpyDeviceToHost, s.st));
         return 0;
     };
     int pending = -1, rc_all = 0;
@@ -516,13 +706,20 @@ static int encode_host_worker(dbde_b200_ctx *c, const uint8_t *frames_host, int 
         CK(cudaStreamSynchronize(s.st));            // the slot's previous chunk has fully drained
         s.first = ci * chunk;
         s.n = nframes - s.first < chunk ? nframes - s.first : chunk;
-        CK(cudaMemcpyAsync(s.d_a, frames_host + px * s.first, px * s.n, cudaMemcpyHostToDevice, s.st));
+        if (in_pageable) {
+            rc_all = relay_h2d(s, s.d_a, frames_host + px * s.first, px * s.n, 0);
+            if (rc_all) break;
+        } else {
+            CK(cudaMemcpyAsync(s.d_a, frames_host + px * s.first, px * s.n, cudaMemcpyHostToDevice, s.st));
+        }
         rc_all = dbde_b200_encode_device(c, s.d_a, W, H, first_index + s.first, s.n, s.d_b + delta, need_b - 32, stride,
                                          s.d_off, s.d_size, s.st);
         if (rc_all) break;
         CK(cudaMemcpyAsync(s.h_size, s.d_size, 8 * (size_t)s.n, cudaMemcpyDeviceToHost, s.st));
-        CK(launch_compact(s.d_b + delta, stride, s.d_size, s.n, s.d_c, s.st));
-        c->launches += 1;
+        if (chunk > 1) {
+            CK(launch_compact(s.d_b + delta, stride, s.d_size, s.n, s.d_c, s.st));
+            c->launches += 1;
+        }
         CK(cudaEventRecord(s.ev, s.st));
         if (pending >= 0) rc_all = finish(pending);
         pending = li;
@@ -582,8 +779,11 @@ static int decode_host_impl(dbde_b200_ctx *c, const uint8_t *stream_host, size_t
     if (need_a < bound_a) need_a = bound_a;
     const size_t need_b = scan_only ? 0 : px * chunk + 32;
     const int ns = nchunks < c->nslots ? nchunks : c->nslots;
+    // pageable caller memory is relayed through pinned bounce buffers (see CopyPool)
+    const bool in_pageable = is_pageable(stream_host), out_pageable = !scan_only && is_pageable(frames_host);
     for (int i = 0; i < ns; i++) {
         int rc = ensure_slot(c, c->slots[i], need_a, need_b, 0, chunk);
+        if (!rc) rc = ensure_bounce(c->slots[i], in_pageable ? need_a : 0, out_pageable ? px * chunk : 0);
         if (rc) return rc;
     }
     // finish(): wait for a chunk's status words, then queue the D2H of its accepted frames.  A
@@ -592,14 +792,22 @@ static int decode_host_impl(dbde_b200_ctx *c, const uint8_t *stream_host, size_t
     auto finish = [&](int ci) -> int {
         HostSlot &s = c->slots[ci % ns];
         CK(cudaEventSynchronize(s.ev));
+        memcpy(status_host + s.first, s.h_status, 4 * (size_t)s.n);
+        if (indices_host) memcpy(indices_host + s.first, s.h_index, 8 * (size_t)s.n);
         if (scan_only) return 0;
         int run0 = 0;
         for (int i = 0; i <= s.n; i++) {
-            const bool ok = i < s.n && status_host[s.first + i] == 0;
+            const bool ok = i < s.n && s.h_status[i] == 0;
             if (!ok) {
-                if (i > run0)
-                    CK(cudaMemcpyAsync(frames_host + px * (s.first + run0), s.d_b + px * run0, px * (size_t)(i - run0),
-                                       cudaMemcpyDeviceToHost, s.st));
+                if (i > run0) {
+                    const size_t bytes = px * (size_t)(i - run0);
+                    if (out_pageable) {
+                        int rc = relay_d2h(s, frames_host + px * (s.first + run0), s.d_b + px * run0, bytes, px * run0);
+                        if (rc) return rc;
+                    } else {
+                        CK(cudaMemcpyAsync(frames_host + px * (s.first + run0), s.d_b + px * run0, bytes, cudaMemcpyDeviceToHost, s.st));
+                    }
+                }
                 run0 = i + 1;
             }
         }
@@ -615,13 +823,17 @@ static int decode_host_impl(dbde_b200_ctx *c, const uint8_t *stream_host, size_t
         const uint64_t b1 = s.first + s.n < nframes ? frame_offsets_host[s.first + s.n] : stream_bytes;
         for (int i = 0; i < s.n; i++) s.h_off[i] = frame_offsets_host[s.first + i] - b0;
         CK(cudaMemcpyAsync(s.d_off, s.h_off, 8 * (size_t)s.n, cudaMemcpyHostToDevice, s.st));
-        CK(cudaMemcpyAsync(s.d_a + delta, stream_host + b0, b1 - b0, cudaMemcpyHostToDevice, s.st));
+        if (in_pageable) {
+            rc_all = relay_h2d(s, s.d_a + delta, stream_host + b0, b1 - b0, 0);
+            if (rc_all) break;
+        } else {
+            CK(cudaMemcpyAsync(s.d_a + delta, stream_host + b0, b1 - b0, cudaMemcpyHostToDevice, s.st));
+        }
         rc_all = decode_device_impl(c, s.d_a + delta, b1 - b0, s.d_off, W, H, s.n, s.d_b, s.d_status, s.d_index, s.st,
                                     scan_only);
         if (rc_all) break;
-        CK(cudaMemcpyAsync(status_host + s.first, s.d_status, 4 * (size_t)s.n, cudaMemcpyDeviceToHost, s.st));
-        if (indices_host)
-            CK(cudaMemcpyAsync(indices_host + s.first, s.d_index, 8 * (size_t)s.n, cudaMemcpyDeviceToHost, s.st));
+        CK(cudaMemcpyAsync(s.h_status, s.d_status, 4 * (size_t)s.n, cudaMemcpyDeviceToHost, s.st));
+        if (indices_host) CK(cudaMemcpyAsync(s.h_index, s.d_index, 8 * (size_t)s.n, cudaMemcpyDeviceToHost, s.st));
         CK(cudaEventRecord(s.ev, s.st));
         if (pending >= 0) rc_all = finish(pending);
         pending = ci;

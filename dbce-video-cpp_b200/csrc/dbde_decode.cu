@@ -310,7 +310,8 @@ __device__ __forceinline__ void dec_unpack_tile(const uint8_t *stage, const uint
     const uint8_t *pay = stage + pres + 8 * (size_t)woff;
     if (__popc(kinds) >= kDecVarMinDepths) {
         if (k > 0) {
-            unpack_rows_var(pay, k, px, m4);
+            if (DBDE_DEC_VAR64 && (pres & 7u) == 0) unpack_rows_var64(pay, k, px, m4);
+            else unpack_rows_var(pay, k, px, m4);
         } else {
 #pragma unroll
             for (int i = 0; i < 16; i++) px[i] = m4;
@@ -404,7 +405,11 @@ __device__ __forceinline__ void dec_producer(const DecParams &P, DecSmemT<NSTAGE
             *reinterpret_cast<int4 *>(&S.ctl[s].part) = make_int4((int)p, 0, pi.f, pi.nt);
             *reinterpret_cast<uint4 *>(&S.ctl[s].pres) =
                 make_uint4(res, kres, mres, (uint32_t)(8 * pi.y0) * (uint32_t)g.W + 8u * (uint32_t)pi.tx0);
-            *reinterpret_cast<int4 *>(&S.ctl[s].y0) = make_int4(pi.y0, pi.tx0, pi.ntx, 0);
+            // pad1: low 32 bits of the global address of the partition's first pixel (its alignment decides the
+            // staged kernel's shared-memory image shift and row-store shapes)
+            const uint32_t pixoff = (uint32_t)(8 * pi.y0) * (uint32_t)g.W + 8u * (uint32_t)pi.tx0;
+            *reinterpret_cast<int4 *>(&S.ctl[s].y0) =
+                make_int4(pi.y0, pi.tx0, pi.ntx, (int)(uint32_t)((uintptr_t)P.frames + (size_t)pi.f * ((size_t)g.W * g.H) + pixoff));
         }
         const uint32_t total = __reduce_add_sync(0xffffffffu, lane < 3 ? len : 0u);
         __syncwarp();
@@ -639,7 +644,8 @@ __global__ void __launch_bounds__(kStgThreads, kStgOut == 1 ? 4 : 3) dbde_decode
                 continue;
             }
             const uint4 c1 = *reinterpret_cast<const uint4 *>(&S.ctl[s].pres);    // pres, kres, mres, pixoff
-            const int y0 = S.ctl[s].y0;
+            const int4 c2 = *reinterpret_cast<const int4 *>(&S.ctl[s].y0);        // y0, tx0, ntx, image address (low 32 bits)
+            const int y0 = c2.x;
             const uint8_t *stage = stages + (size_t)s * kDecStageBytes;
             const bool valid = tid < c0.w;
             uint32_t px[16];
@@ -649,12 +655,9 @@ __global__ void __launch_bounds__(kStgThreads, kStgOut == 1 ? 4 : 3) dbde_decode
 
             const int os = oi % kStgOut;
             if (oi >= kStgOut) mbar_wait(&S.outempty[os], ((oi / kStgOut) - 1) & 1);
-            // The image's global address, recomputed from the partition id: the producer walks the
-            // partitions in the static order blockIdx.x + it * gridDim.x, so frame and band are
-            // block-uniform here and the row alignments below are uniform values.
-            const unsigned up = blockIdx.x + it * gridDim.x;
-            const unsigned uf = up / (unsigned)g.ppf, uq = up - uf * (unsigned)g.ppf;
-            const uint32_t ag = (uint32_t)((uintptr_t)P.frames + (size_t)uf * fbytes + (size_t)(8u * uq * (unsigned)g.G) * (size_t)g.W);
+            // the image's global address (its low bits), from the control block: the same value in every lane,
+            // so the shape branches of the row stores below never diverge
+            const uint32_t ag = (uint32_t)c2.w;
             const uint32_t img = smem_u32(outst) + (uint32_t)os * kStgOutBytes + (ag & 15u);
             const int rows_valid = valid ? min(8, g.H - 8 * (y0 + sb)) : 0;
             uint32_t rp = img + toff;

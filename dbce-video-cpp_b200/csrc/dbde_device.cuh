@@ -342,6 +342,50 @@ __device__ __forceinline__ void unpack_rows_var(const uint8_t *pay, int k, uint3
     }
 }
 
+// The same unpacker for payloads on 8-byte boundaries (the usual case: records are 8-byte aligned and a
+// tile's words are U64s), with the shared-memory traffic cut to what the tile really holds.  The
+// three-word version above issues 24 four-byte loads per tile whatever k is, each with the lanes'
+// addresses scattered over the banks (ncu on the odd-size decoder: 75 % of the shared-memory wavefront
+// budget, about half of it these loads).  Here a lane keeps a 16-byte window {cur, nxt} of two aligned
+// U64s; row r sits at byte (k*r) & 7 of `cur` and ends inside the window (k <= 8); the window moves on by
+// ONE predicated 8-byte load when a row crosses into `nxt` -- k + 1 loads per tile, each word read once.
+// Reads at most 8 bytes past the tile's last word (the stage has that slack).
+#ifndef DBDE_DEC_VAR64
+#define DBDE_DEC_VAR64 1
+#endif
+__device__ __forceinline__ void unpack_rows_var64(const uint8_t *pay, int k, uint32_t (&px)[16], uint32_t m4) {
+    uint32_t addr = smem_u32(pay);
+    const uint32_t fmask = 0xffffffffu >> (32 - 4 * k);
+    const uint32_t c1n = 256u - (1u << k), c2n = 65536u - (1u << (2 * k));
+    const uint32_t kmask2 = ((1u << k) - 1u) * 0x00010001u;
+    uint32_t c_lo, c_hi, n_lo, n_hi;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(c_lo), "=r"(c_hi) : "r"(addr));
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+8];" : "=r"(n_lo), "=r"(n_hi) : "r"(addr));
+    addr += 16u;
+    uint32_t pos = 0;                                               // k * r
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const bool up = (pos & 4u) != 0u;                           // the row starts in the upper half of `cur`
+        const uint32_t t0 = up ? c_hi : c_lo, t1 = up ? n_lo : c_hi, t2 = up ? n_hi : n_lo;
+        const uint32_t sh = pos << 3;                               // funnel shifts use the low 5 bits: 8 * (pos & 3)
+        const uint32_t lo = __funnelshift_r(t0, t1, sh), hi = __funnelshift_r(t1, t2, sh);
+        const uint32_t f0 = lo & fmask;
+        const uint32_t f1 = __funnelshift_rc(lo, hi, 4 * k) & fmask;
+        px[2 * r] = spread4(f0, k, c1n, c2n, kmask2) + m4;
+        px[2 * r + 1] = spread4(f1, k, c1n, c2n, kmask2) + m4;
+        if (r < 7) {
+            const uint32_t nx = pos + (uint32_t)k;
+            if ((pos ^ nx) & 8u) {                                  // the next row starts in `nxt`: slide (predicated)
+                c_lo = n_lo;
+                c_hi = n_hi;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(n_lo), "=r"(n_hi) : "r"(addr));
+                addr += 8u;
+            }
+            pos = nx;
+        }
+    }
+}
+
 // pack: q[16] = the sixteen 4k-bit fields (squeeze4) -> k U64 words at wp (8-byte aligned shared
 // memory).  A 64-bit accumulator takes one k-byte row per step at byte position (k*r) & 7 and is
 // flushed with a predicated store whenever a word completes.

@@ -32,6 +32,7 @@ namespace dbde {
 // A warp with this many different non-zero depths packs with the depth-agnostic row packer.  Measured
 // (mix-2048): never 4.11 TB/s, 4 -> 5.06, 3 -> 5.05; micro-2048 unchanged within noise.
 constexpr int kEncVarMinDepths = 4;
+
 constexpr int kEncRing = 4;        // bookkeeping slots (aggregates, bases): a tile warp is <= 2 partitions ahead of the scan warp
 constexpr int kEncThreads = kTilesPerPart + 64;
 

@@ -58,6 +58,33 @@ void die(const char *what, int rc) {
     abort();
 }
 
+// A per-thread page-locked scratch record for the image-block entry points (dbde_pack_image /
+// dbde_unpack_image add or strip the 20-byte frame header around the GPU's frame records): grown on
+// demand, never zero-filled, and DMA-able, so it costs one memcpy of the record and nothing else.
+struct ScratchRecord {
+    uint8_t *p = nullptr;
+    size_t cap = 0;
+    ~ScratchRecord() {
+        if (p) dbde_b200_host_free(p);
+    }
+};
+uint8_t *scratch_record(size_t bytes) {
+    static thread_local ScratchRecord r;
+    if (r.cap < bytes) {
+        if (r.p) dbde_b200_host_free(r.p);
+        r.p = nullptr;
+        r.cap = 0;
+        void *q = nullptr;
+        if (dbde_b200_host_alloc(bytes + bytes / 4, &q) != 0 || !q) {
+            fprintf(stderr, "dbde_b200: cannot allocate %zu bytes of page-locked scratch: %s\n", bytes, dbde_b200_last_error());
+            abort();
+        }
+        r.p = (uint8_t *)q;
+        r.cap = bytes + bytes / 4;
+    }
+    return r.p;
+}
+
 inline void put32(uint8_t *p, uint32_t v) { memcpy(p, &v, 4); }
 inline void put64(uint8_t *p, uint64_t v) { memcpy(p, &v, 8); }
 inline uint32_t get32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
@@ -143,9 +170,9 @@ size_t dbde_pack_frame(uint64_t index, uint8_t *image, int W, int H, uint8_t *ta
 }
 // reference dbde_util.cpp:137-180: the frame record minus its 20-byte header
 size_t dbde_pack_image(uint8_t *image, int W, int H, uint8_t *target) {
-    std::vector<uint8_t> rec(dbde_b200_frame_record_bound(W, H));
-    const size_t n = dbde_pack_frame(0, image, W, H, rec.data());
-    memcpy(target, rec.data() + 20, n - 20);
+    uint8_t *rec = scratch_record(dbde_b200_frame_record_bound(W, H));
+    const size_t n = dbde_pack_frame(0, image, W, H, rec);
+    memcpy(target, rec + 20, n - 20);
     return n - 20;
 }
 // reference dbde_util.cpp:339-345
@@ -184,11 +211,11 @@ size_t dbde_unpack_image(uint8_t *packed, int W, int H, uint8_t *image) {
     size_t n64 = 0;
     if (!image_block_ok(packed, wh, &n64)) return 0;           // :296,299,303 before anything else is read
     const size_t body = 12 + 2 * wh + 8 * n64;
-    std::vector<uint8_t> rec(20 + body);
+    uint8_t *rec = scratch_record(20 + body);
     frame_header fh = {2, 0, 0};
-    dbde_pack_frame_header(fh, rec.data());
-    memcpy(rec.data() + 20, packed, body);
-    uint8_t *p = rec.data();
+    dbde_pack_frame_header(fh, rec);
+    memcpy(rec + 20, packed, body);
+    uint8_t *p = rec;
     frame_header out = dbde_unpack_frame(&p, W, H, image);
     return out.u64s == 2 ? body : 0;
 }
