@@ -17,6 +17,7 @@
 //                             cropped stores).
 #include "dbde_device.cuh"
 #include "dbde_kernels.h"
+#include <stdlib.h>
 
 namespace dbde {
 
@@ -193,7 +194,8 @@ __global__ void __launch_bounds__(256) dbde_decode_scan_kernel(const DecParams P
 // ------------------------------------------------------------------ main kernel
 struct alignas(16) DecCtl {
     int part;                  // -1 = no more work
-    int skip;                  // frame was rejected by the scan: leave the image untouched
+    int skip;                  // bit 0: frame was rejected by the scan, leave the image untouched; bit 1: every band of
+                               // the partition has its 8 pixel rows inside the frame (no cropped rows)
     int f;                     // frame within the batch
     int nt;                    // tiles in this partition
     uint32_t pres, kres, mres; // residual byte offsets of payload / depth / min inside their hulls
@@ -201,6 +203,7 @@ struct alignas(16) DecCtl {
     int y0, tx0, ntx, pad1;    // first band / first tile column / tile columns (generic path)
     uint32_t wbase[kConsumerWarps];   // word offset of each tile warp inside the partition's payload
 };
+constexpr int kCtlSkip = 1, kCtlAllRows = 2;
 template <int NSTAGES>
 struct DecSmemT {
     uint64_t full[NSTAGES], empty[NSTAGES];
@@ -286,6 +289,162 @@ __device__ __forceinline__ void store_row_generic(uint8_t *rp, uint64_t x, int n
     if (last_in_run && a + (uint32_t)ncol > 8u) store_partial(q + 8, x >> (64u - sh), 0u, a + (uint32_t)ncol - 8u);
 }
 
+// ------------------------------------------------------------------ direct re-aligned row stores (odd sizes)
+// An odd-size frame's rows start at any byte address, so a lane's 8-byte row piece straddles two
+// aligned words.  Consecutive lanes of a band hold consecutive pieces of the same image row, so every
+// lane builds ONE aligned 8-byte word out of its own piece and a neighbour's (a single shuffle plus two
+// funnel shifts) and stores it: a warp's row is one coalesced run of aligned 8-byte stores straight from
+// registers -- no shared-memory image, no store warp, no barrier between tile warps.
+//   alignment a = (row address) & 7 is the same for every lane (bands are multiples of 8 bytes apart);
+//   a == 0      : the piece is the word
+//   a in 1..4   : word at T - a     = [left neighbour's last a bytes | my first 8 - a]   (needs the neighbour's high half)
+//   a in 5..7   : word at T + 8 - a = [my last a bytes | right neighbour's first 8 - a] (needs the neighbour's low half)
+// With W & 7 a template parameter and the partition's first alignment a switch case, every row's
+// shape and shift amount is a compile-time constant.  What the words cannot cover -- the first 8 - a
+// bytes of a run's first lane and the last a bytes of its last lane, per row -- is written once per
+// partition by a boundary pass: the end lanes leave their pixels in a 256-byte scratch of their warp,
+// and lane (run, row, end) stores that piece as at most three naturally aligned narrow stores.
+#ifndef DBDE_DIR_ROWENDS
+#define DBDE_DIR_ROWENDS 1       // run ends stored row by row with compile-time shapes (0: per-partition boundary pass)
+#endif
+#ifndef DBDE_DEC_DIRECT_CS
+#define DBDE_DEC_DIRECT_CS 0     // 1: streaming (evict-first) policy for the re-aligned word stores
+#endif
+#ifndef DBDE_DEC_DIRECT_MINB
+#define DBDE_DEC_DIRECT_MINB 4   // resident CTAs per SM the odd-size kernel is compiled for (register cap 56 at 4)
+#endif
+__device__ __forceinline__ void stg_u64(uint8_t *p, uint32_t lo, uint32_t hi) {
+#if DBDE_DEC_DIRECT_CS
+    asm volatile("st.global.cs.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(lo), "r"(hi) : "memory");
+#else
+    asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(lo), "r"(hi) : "memory");
+#endif
+}
+__device__ __forceinline__ void stg_u32(uint8_t *p, uint32_t v) { asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void stg_u16(uint8_t *p, uint32_t v) {
+    asm volatile("{ .reg .b16 t; cvt.u16.u32 t, %1; st.global.u16 [%0], t; }" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void stg_u8(uint8_t *p, uint32_t v) { asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+constexpr int kDirScratchPerWarp = 256;      // 4 end lanes x 64 pixel bytes
+constexpr uint32_t kDirFull = 1, kDirFirst = 2, kDirLast = 4, kDirPartial = 8;
+struct DirectLane {
+    uint32_t flags;      // kDir* | ncol << 8 | scratch slot of this lane's pixels as a run's first lane << 16 (15 = none)
+                         // | the same as a run's last lane << 20
+    uint32_t item;       // my boundary piece: bit 0 valid, bit 1 end (0 head, 1 tail), bits 4-6 row, bits 8-9 scratch slot,
+                         // bits 16.. tid of the lane whose piece it is
+    uint32_t item_toff;  // that lane's tile offset inside the partition's pixels
+};
+// Who is where in this warp: runs of full-width tiles of one band (at most two per warp when the frame is
+// at least 32 tiles wide), the partial last column, and which boundary piece this lane will write.
+// Warp-wide call (ballots, shuffle).  tx0/ntx: the partition's first tile column and tile columns.
+__device__ __forceinline__ DirectLane direct_setup(const PartGeom &g, int tid, int lane, int stx, uint32_t toff, int tx0,
+                                                   int ntx, int tiles_max) {
+    DirectLane d;
+    const bool ingeo = tid < tiles_max;
+    const int ncol = ingeo ? min(8, g.W - 8 * (tx0 + stx)) : 0;       // lanes past the partition's tiles: nothing
+    const bool full = ingeo && ncol == 8;
+    const bool left_full = lane > 0 && stx > 0;                                           // only a last column can be partial
+    const bool right_full = lane < 31 && stx + 1 < ntx && g.W - 8 * (tx0 + stx + 1) >= 8;
+    const bool first = full && !left_full, last = full && !right_full;
+    d.flags = (full ? kDirFull : 0u) | (first ? kDirFirst : 0u) | (last ? kDirLast : 0u) | (ingeo && ncol < 8 ? kDirPartial : 0u) |
+              ((uint32_t)ncol << 8);
+    const uint32_t mf = __ballot_sync(0xffffffffu, first), ml = __ballot_sync(0xffffffffu, last);
+    const uint32_t below = (1u << lane) - 1u;
+    d.flags |= ((first ? (uint32_t)__popc(mf & below) : 15u) << 16) | ((last ? 2u + (uint32_t)__popc(ml & below) : 15u) << 20);
+    const int run = lane >> 4, r = (lane >> 1) & 7, e = lane & 1;
+    const uint32_t m = e ? ml : mf;
+    const uint32_t m1 = run ? (m & (m - 1u)) : m;                                         // drop the first run's lane
+    const int src = m1 ? __ffs((int)m1) - 1 : 0;
+    d.item = (m1 ? 1u : 0u) | ((uint32_t)e << 1) | ((uint32_t)r << 4) | ((uint32_t)(2 * e + run) << 8) |
+             ((uint32_t)(tid - lane + src) << 16);
+    d.item_toff = __shfl_sync(0xffffffffu, toff, src);
+    return d;
+}
+
+// bytes [O, O + 4) of the 8-byte row {lo, hi}, O a compile-time constant (zero-filled past byte 7)
+template <int O>
+__device__ __forceinline__ uint32_t row_bytes_from(uint32_t lo, uint32_t hi) {
+    if constexpr (O == 0) return lo;
+    else if constexpr (O < 4) return __funnelshift_r(lo, hi, 8 * O);
+    else if constexpr (O == 4) return hi;
+    else return hi >> (8 * (O - 4));
+}
+// The pieces of a row that the aligned words cannot cover, shapes known at compile time: the first
+// N = 8 - A bytes of a run's first lane (ascending sizes from the row address) and the last A bytes of
+// its last lane (descending sizes from the 8-byte boundary), every store naturally aligned.
+template <int A>
+__device__ __forceinline__ void store_row_ends(uint8_t *rp, uint32_t lo, uint32_t hi, bool first, bool last) {
+    constexpr int N = 8 - A;
+    if (first) {
+        if constexpr ((N & 1) != 0) stg_u8(rp, lo);
+        if constexpr ((N & 2) != 0) stg_u16(rp + (N & 1), row_bytes_from<(N & 1)>(lo, hi));
+        if constexpr ((N & 4) != 0) stg_u32(rp + (N & 3), row_bytes_from<(N & 3)>(lo, hi));
+    }
+    if (last) {
+        constexpr int S = 8 - A;
+        if constexpr ((A & 4) != 0) stg_u32(rp + S, row_bytes_from<S>(lo, hi));
+        if constexpr ((A & 2) != 0) stg_u16(rp + S + (A & 4), row_bytes_from<S + (A & 4)>(lo, hi));
+        if constexpr ((A & 1) != 0) stg_u8(rp + S + (A & 6), row_bytes_from<S + (A & 6)>(lo, hi));
+    }
+}
+
+// the eight rows of every lane's tile, alignment of row 0 = A0, frame width & 7 = WM.  Warp-wide call.
+// ENDS: the run ends' leftover pieces are stored here, row by row (else by the per-partition boundary pass).
+template <int WM, int A0, bool ENDS, int R>
+__device__ __forceinline__ void store_rows_direct_from(uint8_t *rp, size_t W, const uint32_t (&px)[16], bool full, bool has_left,
+                                                       bool has_right, bool efirst, bool elast) {
+    if constexpr (R < 8) {
+        constexpr int a = (A0 + R * WM) & 7;
+        const uint32_t lo = px[2 * R], hi = px[2 * R + 1];
+        if constexpr (a == 0) {
+            if (full) stg_u64(rp, lo, hi);
+        } else if constexpr (a <= 4) {
+            const uint32_t ph = __shfl_up_sync(0xffffffffu, hi, 1);
+            const uint32_t w0 = a == 4 ? ph : __funnelshift_l(ph, lo, 8 * a);
+            const uint32_t w1 = a == 4 ? lo : __funnelshift_l(lo, hi, 8 * a);
+            if (has_left) stg_u64(rp - a, w0, w1);
+        } else {
+            const uint32_t nl = __shfl_down_sync(0xffffffffu, lo, 1);
+            const uint32_t w0 = __funnelshift_r(lo, hi, 8 * (8 - a)), w1 = __funnelshift_r(hi, nl, 8 * (8 - a));
+            if (has_right) stg_u64(rp + (8 - a), w0, w1);
+        }
+        if constexpr (ENDS && a != 0) store_row_ends<a>(rp, lo, hi, efirst, elast);
+        store_rows_direct_from<WM, A0, ENDS, R + 1>(rp + W, W, px, full, has_left, has_right, efirst, elast);
+    }
+}
+template <int WM, int A0, bool ENDS>
+__device__ __forceinline__ void store_rows_direct(uint8_t *rp, size_t W, const uint32_t (&px)[16], bool full, bool first,
+                                                  bool last) {
+    store_rows_direct_from<WM, A0, ENDS, 0>(rp, W, px, full, full && !first, full && !last, full && first, full && last);
+}
+template <int WM, bool ENDS>
+__device__ __forceinline__ void store_rows_direct_any(uint32_t a0, uint8_t *rp, size_t W, const uint32_t (&px)[16], bool full,
+                                                      bool first, bool last) {
+    switch (a0 & 7u) {
+        case 0: store_rows_direct<WM, 0, ENDS>(rp, W, px, full, first, last); break;
+        case 1: store_rows_direct<WM, 1, ENDS>(rp, W, px, full, first, last); break;
+        case 2: store_rows_direct<WM, 2, ENDS>(rp, W, px, full, first, last); break;
+        case 3: store_rows_direct<WM, 3, ENDS>(rp, W, px, full, first, last); break;
+        case 4: store_rows_direct<WM, 4, ENDS>(rp, W, px, full, first, last); break;
+        case 5: store_rows_direct<WM, 5, ENDS>(rp, W, px, full, first, last); break;
+        case 6: store_rows_direct<WM, 6, ENDS>(rp, W, px, full, first, last); break;
+        default: store_rows_direct<WM, 7, ENDS>(rp, W, px, full, first, last); break;
+    }
+}
+
+// One boundary piece: bytes [0, 8 - a) of a run's first lane (head, at T) or bytes [8 - a, 8) of its last
+// lane (tail, at T + 8 - a), x = that lane's row.  Sizes 1/2/4 in the order that keeps every store
+// naturally aligned: ascending from T for a head, descending from the 8-byte boundary for a tail.
+__device__ __forceinline__ void store_boundary_piece(uint8_t *T, uint2 x, uint32_t a, uint32_t e) {
+    const uint32_t n = e ? a : 8u - a, s = e ? 8u - a : 0u;
+    const uint32_t o8 = s + (e ? (n & 6u) : 0u), o16 = s + (e ? (n & 4u) : (n & 1u)), o32 = s + (e ? 0u : (n & 3u));
+    auto at = [&](uint32_t o) { return __funnelshift_r((o & 4u) ? x.y : x.x, (o & 4u) ? 0u : x.y, 8u * (o & 3u)); };
+    if (n & 1u) stg_u8(T + o8, at(o8));
+    if (n & 2u) stg_u16(T + o16, at(o16));
+    if (n & 4u) stg_u32(T + o32, at(o32));
+}
+
 // ------------------------------------------------------------------ one lane == one tile: payload -> pixels
 // Reads the tile's depth and minimum from the staged planes and its k words from the staged payload,
 // returns the 64 pixels (+min applied) in px.  Warp-wide call (scan + vote).
@@ -320,10 +479,9 @@ __device__ __forceinline__ void dec_unpack_tile(const uint8_t *stage, const uint
         uint32_t q[16];
         if ((pres & 7u) == 0) load_split_any<8>(k, pay, q);     // the usual case: records on 8-byte boundaries
         else load_split_any<1>(k, pay, q);
-        const uint32_t c1n = 256u - (1u << k), c2n = 65536u - (1u << (2 * k));
-        const uint32_t kmask2 = ((1u << k) - 1u) * 0x00010001u;
+        const SpreadK sk = spread_consts(k);
 #pragma unroll
-        for (int i = 0; i < 16; i++) px[i] = spread4(q[i], k, c1n, c2n, kmask2) + m4;   // +min (dbde_util.cpp:246)
+        for (int i = 0; i < 16; i++) px[i] = spread4(q[i], sk) + m4;   // +min (dbde_util.cpp:246)
     } else {
 #pragma unroll
         for (int i = 0; i < 16; i++) px[i] = m4;                                        // depth 0 (dbde_util.cpp:218-226)
@@ -369,7 +527,7 @@ __device__ __forceinline__ void dec_producer(const DecParams &P, DecSmemT<NSTAGE
         }
         if (status != 0) {
             if (lane == 0) {
-                *reinterpret_cast<int2 *>(&S.ctl[s].part) = make_int2((int)p, 1);
+                *reinterpret_cast<int2 *>(&S.ctl[s].part) = make_int2((int)p, kCtlSkip);
                 mbar_arrive(&S.full[s]);
             }
             b2 = b1;
@@ -402,7 +560,8 @@ __device__ __forceinline__ void dec_producer(const DecParams &P, DecSmemT<NSTAGE
         // lanes 0..2 hold the three residuals: gather them so lane 0 writes the block with two 16-byte stores
         const uint32_t kres = __shfl_sync(0xffffffffu, res, 1), mres = __shfl_sync(0xffffffffu, res, 2);
         if (lane == 0) {
-            *reinterpret_cast<int4 *>(&S.ctl[s].part) = make_int4((int)p, 0, pi.f, pi.nt);
+            *reinterpret_cast<int4 *>(&S.ctl[s].part) =
+                make_int4((int)p, 8 * (pi.y0 + pi.nbands) <= g.H ? kCtlAllRows : 0, pi.f, pi.nt);
             *reinterpret_cast<uint4 *>(&S.ctl[s].pres) =
                 make_uint4(res, kres, mres, (uint32_t)(8 * pi.y0) * (uint32_t)g.W + 8u * (uint32_t)pi.tx0);
             // pad1: low 32 bits of the global address of the partition's first pixel (its alignment decides the
@@ -419,8 +578,12 @@ __device__ __forceinline__ void dec_producer(const DecParams &P, DecSmemT<NSTAGE
     }
 }
 
-template <bool FAST>
-__global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecParams P) {
+// MODE -1: aligned frames (W % 16 == 0, H % 8 == 0, 16-byte aligned base): rows are stored as they are.
+// MODE 0..7 = W & 7: every other geometry; rows are re-aligned across lanes (store_rows_direct) when the
+//           frame is at least 32 tiles wide and the partition has no cropped rows, else stored piecewise.
+template <int MODE>
+__global__ void __launch_bounds__(kDecThreads, MODE < 0 ? 3 : DBDE_DEC_DIRECT_MINB) dbde_decode_kernel(const DecParams P) {
+    constexpr bool FAST = MODE < 0;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     DecSmem &S = *reinterpret_cast<DecSmem *>(smem_raw);
     uint8_t *stages = smem_raw + ((sizeof(DecSmem) + 127) & ~127);
@@ -448,18 +611,27 @@ __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecPa
         }
         const uint32_t toff = (uint32_t)(8 * sb) * (uint32_t)g.W + 8u * (uint32_t)stx;   // my tile inside a partition's pixels
         const size_t rowstride = (size_t)g.W;
+        // direct re-aligned stores: the warp's run structure is fixed for full-width partitions and is
+        // worked out per partition for band segments of wider frames (the last segment is shorter)
+        const bool direct_geom = !FAST && g.w >= 32;
+        DirectLane dl = {0u, 0u, 0u};
+        if (direct_geom && g.nseg == 1) dl = direct_setup(g, tid, lane, stx, toff, 0, g.w, g.G * g.w);
+        uint8_t *scr = stages + (size_t)kDecStages * kDecStageBytes + (size_t)warp * kDirScratchPerWarp;
+        (void)scr;
         for (unsigned it = 0;; it++) {
             const int s = it % kDecStages;
             const uint32_t ph = (it / kDecStages) & 1;
             mbar_wait(&S.full[s], ph);
-            const int4 c0 = *reinterpret_cast<const int4 *>(&S.ctl[s].part);      // part, skip, f, nt
+            const int4 c0 = *reinterpret_cast<const int4 *>(&S.ctl[s].part);      // part, flags, f, nt
             if (c0.x < 0) break;
-            if (c0.y) {
+            if (c0.y & kCtlSkip) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&S.empty[s]);
                 continue;
             }
             const uint4 c1 = *reinterpret_cast<const uint4 *>(&S.ctl[s].pres);    // pres, kres, mres, pixoff
+            int4 c2 = make_int4(0, 0, 0, 0);
+            if (!FAST) c2 = *reinterpret_cast<const int4 *>(&S.ctl[s].y0);        // y0, tx0, ntx, image address (low 32 bits)
             const uint8_t *stage = stages + (size_t)s * kDecStageBytes;
             const bool valid = tid < c0.w;
             uint32_t px[16];
@@ -468,7 +640,8 @@ __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecPa
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.empty[s]);       // payload is in registers: free the stage early
 
-            uint8_t *rp = P.frames + (size_t)c0.z * fbytes + (c1.w + toff);
+            uint8_t *const part0 = P.frames + (size_t)c0.z * fbytes + c1.w;       // the partition's first pixel
+            uint8_t *rp = part0 + toff;
             if (FAST) {
                 // no edges, 8-byte aligned rows: lane t stores 8 bytes of each row, a warp 256 contiguous bytes
                 if (valid) {
@@ -478,9 +651,58 @@ __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecPa
                         rp += rowstride;
                     }
                 }
+            } else if (direct_geom && (c0.y & kCtlAllRows)) {
+                if (g.nseg > 1) dl = direct_setup(g, tid, lane, stx, toff, c2.y, c2.z, c2.z);
+                const bool full = valid && (dl.flags & kDirFull);
+#if DBDE_DIR_ROWENDS
+                store_rows_direct_any<(MODE < 0 ? 0 : MODE), true>((uint32_t)c2.w, rp, rowstride, px, full, (dl.flags & kDirFirst) != 0,
+                                                                   (dl.flags & kDirLast) != 0);
+#else
+                // the end lanes of every run leave their pixels where the boundary pass finds them
+                {
+                    const uint32_t df = (dl.flags >> 16) & 15u, dt = (dl.flags >> 20) & 15u;
+                    if (df != 15u) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            *reinterpret_cast<uint4 *>(scr + 64 * df + 16 * j) = make_uint4(px[4 * j], px[4 * j + 1], px[4 * j + 2], px[4 * j + 3]);
+                    }
+                    if (dt != 15u) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            *reinterpret_cast<uint4 *>(scr + 64 * dt + 16 * j) = make_uint4(px[4 * j], px[4 * j + 1], px[4 * j + 2], px[4 * j + 3]);
+                    }
+                }
+                __syncwarp();
+                store_rows_direct_any<(MODE < 0 ? 0 : MODE), false>((uint32_t)c2.w, rp, rowstride, px, full, (dl.flags & kDirFirst) != 0,
+                                                                    (dl.flags & kDirLast) != 0);
+#endif
+                if (valid && (dl.flags & kDirPartial)) {
+                    // the frame's last tile column when W % 8 != 0 (dbde_util.cpp:281-289): its columns byte by byte
+                    const int ncol = (int)((dl.flags >> 8) & 15u);
+                    for (int c = 0; c < ncol; c++) {
+                        const uint32_t sh = 8u * (uint32_t)(c & 3);
+                        uint8_t *q = rp + c;
+#pragma unroll
+                        for (int r = 0; r < 8; r++) {
+                            stg_u8(q, ((c & 4) ? px[2 * r + 1] : px[2 * r]) >> sh);
+                            q += rowstride;
+                        }
+                    }
+                }
+#if !DBDE_DIR_ROWENDS
+                if ((dl.item & 1u) && (int)(dl.item >> 16) < c0.w) {
+                    const uint32_t e = (dl.item >> 1) & 1u, r = (dl.item >> 4) & 7u, slot = (dl.item >> 8) & 3u;
+                    const uint32_t rW = r * (uint32_t)g.W;
+                    const uint32_t a = ((uint32_t)c2.w + rW) & 7u;
+                    if (a) {
+                        const uint2 x = *reinterpret_cast<const uint2 *>(scr + 64 * slot + 8 * r);
+                        store_boundary_piece(part0 + dl.item_toff + rW, x, a, e);
+                    }
+                }
+                __syncwarp();                              // the scratch is read before the next partition overwrites it
+#endif
             } else {
                 // crop the padding (dbde_util.cpp:281-289): only rows < H and columns < W are written
-                const int4 c2 = *reinterpret_cast<const int4 *>(&S.ctl[s].y0);      // y0, tx0, ntx
                 const int rows_valid = valid ? min(8, g.H - 8 * (c2.x + sb)) : 0;
                 const int ncol = min(8, g.W - 8 * (c2.y + stx));
                 const bool first_in_run = lane == 0 || stx == 0;
@@ -514,6 +736,12 @@ __global__ void __launch_bounds__(kDecThreads, 3) dbde_decode_kernel(const DecPa
 // re-aligns row by row (2 x LDS.128 + 4 funnel shifts + one 16-byte global store per chunk): correct, but
 // 2x SLOWER (0.85 vs 0.43 ms per 1000 frames) -- ~90 instructions per image row on ONE warp that gets a
 // seventh of its scheduler; spread over the tile warps it would cost what the narrow stores cost now.
+#ifndef DBDE_STG_EDGE_OLD
+#define DBDE_STG_EDGE_OLD 0
+#endif
+#ifndef DBDE_STG_STATIC
+#define DBDE_STG_STATIC 1        // compile-time row shapes in the staged decoder (0: per-row alignment tests, for A/B runs)
+#endif
 constexpr int kStgStages = 2;                                    // input stages
 // One output image per CTA: 2 x 17 KiB in + 16.5 KiB out = 4 CTAs/SM.  Measured against two images (3 CTAs/SM):
 // +7-10 % on every 1001x1003 workload (mix 3.54 -> 3.81 TB/s) -- a fourth CTA hides more than a second image does.
@@ -562,6 +790,53 @@ __device__ __forceinline__ void sts_row8(uint32_t addr, uint32_t a, uint32_t lo,
     }
 }
 
+// The eight rows of a tile with every alignment known at compile time (WM = W & 7, A0 = alignment of row 0,
+// a switch case per partition): each row is its naturally aligned pieces at immediate offsets with constant
+// shifts -- 8 | 4+4 | 2+4+2 | 1+2+4+1 | 1+4+2+1 -- and no alignment test is executed per row.
+template <int WM, int A0>
+__device__ __forceinline__ void sts_rows_static(uint32_t rp, uint32_t W, const uint32_t (&px)[16]) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const int a = (A0 + r * WM) & 7;                       // compile-time after unrolling
+        const uint32_t lo = px[2 * r], hi = px[2 * r + 1];
+        if (a == 0) {
+            sts_v2u32(rp, lo, hi);
+        } else if (a == 4) {
+            sts_u32(rp, lo);
+            sts_u32(rp + 4, hi);
+        } else if ((a & 1) == 0) {                             // 2, 6
+            sts_u16(rp, lo);
+            sts_u32(rp + 2, __funnelshift_r(lo, hi, 16));
+            sts_u16(rp + 6, hi >> 16);
+        } else if ((a & 3) == 1) {                             // 1, 5: rp + 3 is the 4-byte boundary
+            sts_u8(rp, lo);
+            sts_u16(rp + 1, lo >> 8);
+            sts_u32(rp + 3, __funnelshift_r(lo, hi, 24));
+            sts_u8(rp + 7, hi >> 24);
+        } else {                                               // 3, 7: rp + 1 is the 4-byte boundary
+            sts_u8(rp, lo);
+            sts_u32(rp + 1, __funnelshift_r(lo, hi, 8));
+            sts_u16(rp + 5, hi >> 8);
+            sts_u8(rp + 7, hi >> 24);
+        }
+        rp += W;
+    }
+}
+template <int WM>
+__device__ __forceinline__ void sts_rows_static_any(uint32_t a0, uint32_t rp, uint32_t W, const uint32_t (&px)[16]) {
+    switch (a0 & 7u) {
+        case 0: sts_rows_static<WM, 0>(rp, W, px); break;
+        case 1: sts_rows_static<WM, 1>(rp, W, px); break;
+        case 2: sts_rows_static<WM, 2>(rp, W, px); break;
+        case 3: sts_rows_static<WM, 3>(rp, W, px); break;
+        case 4: sts_rows_static<WM, 4>(rp, W, px); break;
+        case 5: sts_rows_static<WM, 5>(rp, W, px); break;
+        case 6: sts_rows_static<WM, 6>(rp, W, px); break;
+        default: sts_rows_static<WM, 7>(rp, W, px); break;
+    }
+}
+
+template <int WM>
 __global__ void __launch_bounds__(kStgThreads, kStgOut == 1 ? 4 : 3) dbde_decode_staged_kernel(const DecParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     StgSmem &S = *reinterpret_cast<StgSmem *>(smem_raw);
@@ -598,7 +873,7 @@ __global__ void __launch_bounds__(kStgThreads, kStgOut == 1 ? 4 : 3) dbde_decode
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.empty[s]);
             if (c0.x < 0) break;
-            if (c0.y) continue;
+            if (c0.y & kCtlSkip) continue;
             const int os = oi % kStgOut;
             const int nbands = c0.w / g.w;
             const int rows = min(8 * nbands, g.H - 8 * y0);
@@ -638,7 +913,7 @@ __global__ void __launch_bounds__(kStgThreads, kStgOut == 1 ? 4 : 3) dbde_decode
             mbar_wait(&S.full[s], (it / kStgStages) & 1);
             const int4 c0 = *reinterpret_cast<const int4 *>(&S.ctl[s].part);      // part, skip, f, nt
             if (c0.x < 0) break;
-            if (c0.y) {
+            if (c0.y & kCtlSkip) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&S.empty[s]);
                 continue;
@@ -662,6 +937,9 @@ __global__ void __launch_bounds__(kStgThreads, kStgOut == 1 ? 4 : 3) dbde_decode
             const int rows_valid = valid ? min(8, g.H - 8 * (y0 + sb)) : 0;
             uint32_t rp = img + toff;
             if (rows_valid == 8 && ncol == 8) {
+#if DBDE_STG_STATIC
+                sts_rows_static_any<WM>(ag, rp, (uint32_t)g.W, px);      // `ag & 7` is the same in every lane: a uniform switch
+#else
                 uint32_t a = ag;                            // image row alignment (tiles are 8 bytes apart: same for every lane)
 #pragma unroll
                 for (int r = 0; r < 8; r++) {
@@ -669,9 +947,12 @@ __global__ void __launch_bounds__(kStgThreads, kStgOut == 1 ? 4 : 3) dbde_decode
                     rp += g.W;
                     a += g.W;
                 }
+#endif
             } else {
                 // last tile column of an odd-width frame / last band of an odd-height one: only the
-                // valid columns and rows (dbde_util.cpp:281-289); a few lanes per partition
+                // valid columns and rows (dbde_util.cpp:281-289); a few lanes per partition.  Column by
+                // column, so the common one-or-two-column edge costs one or two passes over the rows.
+#if DBDE_STG_EDGE_OLD
 #pragma unroll
                 for (int r = 0; r < 8; r++) {
                     if (r < rows_valid) {
@@ -680,6 +961,19 @@ __global__ void __launch_bounds__(kStgThreads, kStgOut == 1 ? 4 : 3) dbde_decode
                     }
                     rp += g.W;
                 }
+#else
+                // (lanes past the partition's tiles come here too, with rows_valid == 0: they must not loop)
+                const int nc = rows_valid > 0 ? ncol : 0;
+                for (int c = 0; c < nc; c++) {
+                    const uint32_t sh = 8u * (uint32_t)(c & 3);
+                    uint32_t q = rp + (uint32_t)c;
+#pragma unroll
+                    for (int r = 0; r < 8; r++) {
+                        if (r < rows_valid) sts_u8(q, ((c & 4) ? px[2 * r + 1] : px[2 * r]) >> sh);
+                        q += g.W;
+                    }
+                }
+#endif
             }
             fence_proxy_async();                           // my generic-proxy writes, then the store warp's bulk read
             __syncwarp();
@@ -691,8 +985,9 @@ __global__ void __launch_bounds__(kStgThreads, kStgOut == 1 ? 4 : 3) dbde_decode
 
 size_t dec_smem_bytes(const PartGeom &g) {
     (void)g;
-    return ((sizeof(DecSmem) + 127) & ~(size_t)127) + (size_t)kDecStages * kDecStageBytes;
+    return ((sizeof(DecSmem) + 127) & ~(size_t)127) + (size_t)kDecStages * kDecStageBytes + kConsumerWarps * kDirScratchPerWarp;
 }
+static size_t dec_fast_smem_bytes() { return ((sizeof(DecSmem) + 127) & ~(size_t)127) + (size_t)kDecStages * kDecStageBytes; }
 
 cudaError_t launch_decode_scan(const DecParams &P, cudaStream_t stream) {
     if (P.nframes <= 0) return cudaSuccess;
@@ -719,12 +1014,41 @@ static cudaError_t launch_persistent(Kern kern, const DecParams &P, int threads,
     return cudaGetLastError();
 }
 
+// Which kernel unpacks odd-size frames whose partitions span the full width (W <= 2048): "staged"
+// (image built in shared memory, one bulk store per partition: the default, 5-25 % faster on every
+// 1001x1003 workload) or "direct" (re-aligned row stores from registers, the kernel that serves wider odd
+// frames).  DBDE_B200_ODD_DECODE=staged|direct picks one for tests and A/B measurements.
+static bool odd_decode_staged() {
+    const char *e = getenv("DBDE_B200_ODD_DECODE");       // read per launch: tests switch it inside one process
+    return !(e && e[0] == 'd');
+}
+
 cudaError_t launch_decode(const DecParams &P, bool fast, int num_sms, cudaStream_t stream) {
-    if (fast) return launch_persistent(dbde_decode_kernel<true>, P, kDecThreads, dec_smem_bytes(P.g), num_sms, stream);
-    // odd sizes: full-width partitions (W <= 2048) stage their pixels and store them in bulk; wider
-    // odd frames (band segments are not contiguous in the frame) keep the direct generic stores
-    if (P.g.nseg == 1) return launch_persistent(dbde_decode_staged_kernel, P, kStgThreads, stg_smem_bytes(), num_sms, stream);
-    return launch_persistent(dbde_decode_kernel<false>, P, kDecThreads, dec_smem_bytes(P.g), num_sms, stream);
+    const size_t smem = dec_smem_bytes(P.g);
+    if (fast) return launch_persistent(dbde_decode_kernel<-1>, P, kDecThreads, dec_fast_smem_bytes(), num_sms, stream);
+    if (P.g.nseg == 1 && odd_decode_staged()) {
+        const size_t ss = stg_smem_bytes();
+        switch (P.g.W & 7) {
+            case 0: return launch_persistent(dbde_decode_staged_kernel<0>, P, kStgThreads, ss, num_sms, stream);
+            case 1: return launch_persistent(dbde_decode_staged_kernel<1>, P, kStgThreads, ss, num_sms, stream);
+            case 2: return launch_persistent(dbde_decode_staged_kernel<2>, P, kStgThreads, ss, num_sms, stream);
+            case 3: return launch_persistent(dbde_decode_staged_kernel<3>, P, kStgThreads, ss, num_sms, stream);
+            case 4: return launch_persistent(dbde_decode_staged_kernel<4>, P, kStgThreads, ss, num_sms, stream);
+            case 5: return launch_persistent(dbde_decode_staged_kernel<5>, P, kStgThreads, ss, num_sms, stream);
+            case 6: return launch_persistent(dbde_decode_staged_kernel<6>, P, kStgThreads, ss, num_sms, stream);
+            default: return launch_persistent(dbde_decode_staged_kernel<7>, P, kStgThreads, ss, num_sms, stream);
+        }
+    }
+    switch (P.g.W & 7) {
+        case 0: return launch_persistent(dbde_decode_kernel<0>, P, kDecThreads, smem, num_sms, stream);
+        case 1: return launch_persistent(dbde_decode_kernel<1>, P, kDecThreads, smem, num_sms, stream);
+        case 2: return launch_persistent(dbde_decode_kernel<2>, P, kDecThreads, smem, num_sms, stream);
+        case 3: return launch_persistent(dbde_decode_kernel<3>, P, kDecThreads, smem, num_sms, stream);
+        case 4: return launch_persistent(dbde_decode_kernel<4>, P, kDecThreads, smem, num_sms, stream);
+        case 5: return launch_persistent(dbde_decode_kernel<5>, P, kDecThreads, smem, num_sms, stream);
+        case 6: return launch_persistent(dbde_decode_kernel<6>, P, kDecThreads, smem, num_sms, stream);
+        default: return launch_persistent(dbde_decode_kernel<7>, P, kDecThreads, smem, num_sms, stream);
+    }
 }
 
 }  // namespace dbde

@@ -273,13 +273,48 @@ __device__ __forceinline__ uint32_t squeeze4(uint32_t d, uint32_t c1, uint32_t c
     uint32_t p = d + odd * c1;
     return p + (p >> 16) * c2;
 }
-// inverse: one 4k-bit field -> 4 bytes
-//   q = l + 2^2k*h -> p = q + h*(65536 - 2^2k);   p = e + 2^k*o (per u16) -> w = p + o*(256 - 2^k)
-__device__ __forceinline__ uint32_t spread4(uint32_t q, int k, uint32_t c1n, uint32_t c2n, uint32_t kmask2) {
-    uint32_t p = q + (q >> (2 * k)) * c2n;
-    uint32_t odd = (p >> k) & kmask2;                // kmask2 = ((1<<k)-1) * 0x00010001
-    return p + odd * c1n;
+// inverse: one 4k-bit field -> 4 bytes, as two mask-and-multiply-add steps with no shifts:
+//   q = l + 2^2k*h  ->  p = l + 2^16*h = q + (q & hmask) * (2^(16-2k) - 1)       hmask = bits [2k, 4k)
+//   p = e + 2^k*o (per u16)  ->  w = e + 2^8*o = p + (p & omask) * (2^(8-k) - 1)   omask = bits [k, 2k) of both halves
+// The masked values are the moved fields still at their old places, so the multipliers are the
+// integers 2^(distance) - 1 and no product leaves 32 bits (h*c2s < 2^(16+2k), o*c1s < 2^(24+k)).
+// Four instructions per word (LOP3, IMAD, LOP3, IMAD); the first version shifted the fields down
+// before multiplying (SHF, IMAD, SHF, LOP3, IMAD).  q must be zero above bit 4k.
+struct SpreadK {
+    uint32_t hmask, c2s, omask, c1s;
+};
+__device__ __forceinline__ SpreadK spread_consts(int k) {           // k = 1..8
+    SpreadK s;
+    s.hmask = ((1u << (2 * k)) - 1u) << (2 * k);
+    s.c2s = (1u << (16 - 2 * k)) - 1u;
+    s.omask = (((1u << k) - 1u) << k) * 0x00010001u;
+    s.c1s = (1u << (8 - k)) - 1u;
+    return s;
 }
+#ifndef DBDE_SPREAD_OLD
+#define DBDE_SPREAD_OLD 1
+#endif
+#if DBDE_SPREAD_OLD
+__device__ __forceinline__ SpreadK spread_consts_old(int k) {
+    SpreadK s;
+    s.hmask = (uint32_t)k;
+    s.c2s = 65536u - (1u << (2 * k));
+    s.omask = ((1u << k) - 1u) * 0x00010001u;
+    s.c1s = 256u - (1u << k);
+    return s;
+}
+#define spread_consts spread_consts_old
+__device__ __forceinline__ uint32_t spread4(uint32_t q, const SpreadK &s) {
+    const uint32_t p = q + (q >> (2 * s.hmask)) * s.c2s;
+    const uint32_t odd = (p >> s.hmask) & s.omask;
+    return p + odd * s.c1s;
+}
+#else
+__device__ __forceinline__ uint32_t spread4(uint32_t q, const SpreadK &s) {
+    const uint32_t p = q + (q & s.hmask) * s.c2s;
+    return p + (p & s.omask) * s.c1s;
+}
+#endif
 
 // Concatenate sixteen 4K-bit fields LSB-first into K little-endian U64 words (2K u32 halves).
 // Everything is compile-time after unrolling.  Fields never overlap, so "or" is "add" and a
@@ -326,8 +361,7 @@ __device__ __forceinline__ void split_fields(const uint32_t (&x)[16], uint32_t (
 __device__ __forceinline__ void unpack_rows_var(const uint8_t *pay, int k, uint32_t (&px)[16], uint32_t m4) {
     const uint32_t a0 = smem_u32(pay);
     const uint32_t fmask = 0xffffffffu >> (32 - 4 * k);
-    const uint32_t c1n = 256u - (1u << k), c2n = 65536u - (1u << (2 * k));
-    const uint32_t kmask2 = ((1u << k) - 1u) * 0x00010001u;
+    const SpreadK sk = spread_consts(k);
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         const uint32_t a = a0 + (uint32_t)(k * r);
@@ -337,8 +371,8 @@ __device__ __forceinline__ void unpack_rows_var(const uint8_t *pay, int k, uint3
         const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
         const uint32_t f0 = lo & fmask;
         const uint32_t f1 = __funnelshift_rc(lo, hi, 4 * k) & fmask;  // clamped: 4k == 32 selects hi
-        px[2 * r] = spread4(f0, k, c1n, c2n, kmask2) + m4;
-        px[2 * r + 1] = spread4(f1, k, c1n, c2n, kmask2) + m4;
+        px[2 * r] = spread4(f0, sk) + m4;
+        px[2 * r + 1] = spread4(f1, sk) + m4;
     }
 }
 
@@ -356,8 +390,7 @@ __device__ __forceinline__ void unpack_rows_var(const uint8_t *pay, int k, uint3
 __device__ __forceinline__ void unpack_rows_var64(const uint8_t *pay, int k, uint32_t (&px)[16], uint32_t m4) {
     uint32_t addr = smem_u32(pay);
     const uint32_t fmask = 0xffffffffu >> (32 - 4 * k);
-    const uint32_t c1n = 256u - (1u << k), c2n = 65536u - (1u << (2 * k));
-    const uint32_t kmask2 = ((1u << k) - 1u) * 0x00010001u;
+    const SpreadK sk = spread_consts(k);
     uint32_t c_lo, c_hi, n_lo, n_hi;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(c_lo), "=r"(c_hi) : "r"(addr));
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+8];" : "=r"(n_lo), "=r"(n_hi) : "r"(addr));
@@ -371,8 +404,8 @@ __device__ __forceinline__ void unpack_rows_var64(const uint8_t *pay, int k, uin
         const uint32_t lo = __funnelshift_r(t0, t1, sh), hi = __funnelshift_r(t1, t2, sh);
         const uint32_t f0 = lo & fmask;
         const uint32_t f1 = __funnelshift_rc(lo, hi, 4 * k) & fmask;
-        px[2 * r] = spread4(f0, k, c1n, c2n, kmask2) + m4;
-        px[2 * r + 1] = spread4(f1, k, c1n, c2n, kmask2) + m4;
+        px[2 * r] = spread4(f0, sk) + m4;
+        px[2 * r + 1] = spread4(f1, sk) + m4;
         if (r < 7) {
             const uint32_t nx = pos + (uint32_t)k;
             if ((pos ^ nx) & 8u) {                                  // the next row starts in `nxt`: slide (predicated)
@@ -392,20 +425,23 @@ __device__ __forceinline__ void unpack_rows_var64(const uint8_t *pay, int k, uin
 __device__ __forceinline__ void pack_rows_var(const uint32_t (&q)[16], int k, uint8_t *wp) {
     uint64_t acc = 0;
     uint32_t addr = smem_u32(wp);
-    const uint32_t k4 = 4u * (uint32_t)k;
+    const uint32_t k4 = 4u * (uint32_t)k, k8 = 8u * (uint32_t)k;
+    uint32_t s = 0;                                                   // bit position inside the open word: 0, 8, .., 56
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         // the row as a 64-bit value: q[2r] | q[2r+1] << 4k   (clamped funnel shifts: 4k == 32 is legal)
         const uint32_t rlo = q[2 * r] | __funnelshift_lc(0u, q[2 * r + 1], k4);
         const uint32_t rhi = __funnelshift_lc(q[2 * r + 1], 0u, k4);
         const uint64_t row = ((uint64_t)rhi << 32) | rlo;
-        const uint32_t s = (8u * (uint32_t)(k * r)) & 63u;            // bit position inside the open word: 0, 8, .., 56
         acc |= row << s;
-        if (s + 8u * (uint32_t)k >= 64u) {                            // the open word is complete (predicated, not a branch)
+        const uint32_t t = s + k8;
+        if (t >= 64u) {                                               // the open word is complete (predicated, not a branch)
             asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(acc) : "memory");
             addr += 8u;
-            acc = s ? row >> (64u - s) : 0ull;                        // spill-over (s == 0 only at depth 8: none)
+            // spill-over = row >> (64 - s); PTX shifts clamp at the register width, so s == 0 (depth 8) gives 0
+            asm("shr.b64 %0, %1, %2;" : "=l"(acc) : "l"(row), "r"(64u - s));
         }
+        s = t & 63u;
     }
 }
 

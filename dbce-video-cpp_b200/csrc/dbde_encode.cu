@@ -33,6 +33,9 @@ namespace dbde {
 // (mix-2048): never 4.11 TB/s, 4 -> 5.06, 3 -> 5.05; micro-2048 unchanged within noise.
 constexpr int kEncVarMinDepths = 4;
 
+#ifndef DBDE_ENC_COPY16
+#define DBDE_ENC_COPY16 1       // copy-out with 16-byte stores (0: 8-byte stores, for A/B runs)
+#endif
 constexpr int kEncRing = 4;        // bookkeeping slots (aggregates, bases): a tile warp is <= 2 partitions ahead of the scan warp
 constexpr int kEncThreads = kTilesPerPart + 64;
 
@@ -88,7 +91,52 @@ constexpr int kWidePitch = 8 * kTilesPerPart;
 // CONTIG: odd sizes whose partitions span the full width (W <= 2048): the partition's pixels are one
 //        contiguous byte range of the frame, staged with ONE bulk copy of its 16-byte hull at row
 //        pitch W; a lane's row is then `first row + r * W`, read as aligned words + funnel shift.
-template <bool FAST, bool WIDE, bool CONTIG>
+// CONTIG row loads with every shape known at compile time: WM = W & 7, A0 = alignment of the tile's row 0
+// (the same for every lane: tiles and bands are multiples of 8 bytes apart).  A row at byte alignment a is
+// one 8-byte load (a == 0), two 4-byte loads (a == 4), or an 8-byte and a 4-byte load of the three aligned
+// words it touches plus two funnel shifts by a constant.
+template <int WM, int A0>
+__device__ __forceinline__ void load_rows_contig(uint32_t addr, uint32_t W, uint32_t (&px)[16]) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const int a = (A0 + r * WM) & 7;                       // compile-time after unrolling
+        const uint32_t b = addr - (uint32_t)a;                 // 8-byte aligned
+        uint32_t w0, w1, w2;
+        if (a == 0) {
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(px[2 * r]), "=r"(px[2 * r + 1]) : "r"(b));
+        } else if (a == 4) {
+            asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(px[2 * r]) : "r"(b));
+            asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(px[2 * r + 1]) : "r"(b));
+        } else if (a < 4) {
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(b));
+            asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(b));
+            px[2 * r] = __funnelshift_r(w0, w1, 8 * a);
+            px[2 * r + 1] = __funnelshift_r(w1, w2, 8 * a);
+        } else {
+            asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w0) : "r"(b));
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+8];" : "=r"(w1), "=r"(w2) : "r"(b));
+            px[2 * r] = __funnelshift_r(w0, w1, 8 * (a - 4));
+            px[2 * r + 1] = __funnelshift_r(w1, w2, 8 * (a - 4));
+        }
+        addr += W;
+    }
+}
+template <int WM>
+__device__ __forceinline__ void load_rows_contig_any(uint32_t addr, uint32_t W, uint32_t (&px)[16]) {
+    switch (addr & 7u) {
+        case 0: load_rows_contig<WM, 0>(addr, W, px); break;
+        case 1: load_rows_contig<WM, 1>(addr, W, px); break;
+        case 2: load_rows_contig<WM, 2>(addr, W, px); break;
+        case 3: load_rows_contig<WM, 3>(addr, W, px); break;
+        case 4: load_rows_contig<WM, 4>(addr, W, px); break;
+        case 5: load_rows_contig<WM, 5>(addr, W, px); break;
+        case 6: load_rows_contig<WM, 6>(addr, W, px); break;
+        default: load_rows_contig<WM, 7>(addr, W, px); break;
+    }
+}
+
+// WM: W & 7 for the CONTIG kernel (compile-time row shapes), 0 otherwise.
+template <bool FAST, bool WIDE, bool CONTIG, int WM = 0>
 __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     EncSmem &S = *reinterpret_cast<EncSmem *>(smem_raw);
@@ -282,6 +330,36 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
             // ---- this warp's words, by this warp: one coalesced run per warp
             uint8_t *dst = frame + fixed + 8 * ((size_t)b.z + S.wbase[ds][warp]);
             const uint32_t n = d_wtot;
+#if DBDE_ENC_COPY16
+            if (((uintptr_t)dst & 7) == 0) {
+                // 16-byte stores: one leading word when the run starts on an odd word, then pairs of words
+                // (the warp's staging region is 16-byte aligned, so an even start also loads 16 bytes at a time)
+                const uint32_t head = ((uint32_t)(uintptr_t)dst >> 3) & 1u;
+                const uint32_t npair = (n - min(head, n)) >> 1;
+                if (head) {
+                    if (lane == 0 && n) st_stream_u64(dst, *reinterpret_cast<const uint64_t *>(src));
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (32u * j >= npair) break;
+                        const uint32_t i = lane + 32u * j;
+                        if (i < npair) {
+                            const uint2 lo = *reinterpret_cast<const uint2 *>(src + 8 + 16 * i);
+                            const uint2 hi = *reinterpret_cast<const uint2 *>(src + 16 + 16 * i);
+                            st_stream_v4u32(dst + 8 + 16 * i, make_uint4(lo.x, lo.y, hi.x, hi.y));
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (32u * j >= npair) break;
+                        const uint32_t i = lane + 32u * j;
+                        if (i < npair) st_stream_v4u32(dst + 16 * i, *reinterpret_cast<const uint4 *>(src + 16 * i));
+                    }
+                }
+                // the last word of a run with an odd number of words after the head
+                if (lane == 31 && n > head && ((n - head) & 1u))
+                    st_stream_u64(dst + 8 * (n - 1), *reinterpret_cast<const uint64_t *>(src + 8 * (n - 1)));
+#else
             if (((uintptr_t)dst & 7) == 0) {
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
@@ -289,6 +367,7 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
                     if (lane + 32u * j < n)
                         st_stream_u64(dst + 8 * (lane + 32 * j), *reinterpret_cast<const uint64_t *>(src + 8 * (lane + 32 * j)));
                 }
+#endif
             } else {
                 for (uint32_t i = lane; i < 8 * n; i += 32) dst[i] = src[i];
             }
@@ -334,16 +413,25 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
                     asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(a & ~3u));
                     return make_uint2(__funnelshift_r(w0, w1, a << 3), __funnelshift_r(w1, w2, a << 3));
                 };
-                if (!valid || (rows_valid == 8 && ncol == 8)) {
+                // `addr & 7` is the same in every lane (tiles and bands are multiples of 8 bytes apart), so the
+                // switch inside is a uniform branch.  A tile of the last column (ncol < 8) loads its rows the same
+                // way -- the bytes past the row end are the next row's, or stage slack -- and then repeats its
+                // last valid pixel over them (dbde_util.cpp:119-127): one byte-broadcast and two selects per row.
+                if (!valid || rows_valid == 8) {
+                    load_rows_contig_any<WM>(addr, (uint32_t)g.W, px);
+                    if (ncol < 8) {
+                        const uint32_t bsel = 0x1111u * (uint32_t)(ncol - 1);                       // PRMT selector: byte ncol-1 of {lo, hi} four times
+                        const uint32_t klo = ncol >= 4 ? 0xffffffffu : (1u << (8 * ncol)) - 1u;     // bytes of the low / high word that are real pixels
+                        const uint32_t khi = ncol <= 4 ? 0u : (1u << (8 * (ncol - 4))) - 1u;
 #pragma unroll
-                    for (int r = 0; r < 8; r++) {
-                        const uint2 v = load8(addr);
-                        addr += (uint32_t)g.W;
-                        px[2 * r] = v.x;
-                        px[2 * r + 1] = v.y;
+                        for (int r = 0; r < 8; r++) {
+                            const uint32_t fill = __byte_perm(px[2 * r], px[2 * r + 1], bsel);
+                            px[2 * r] = (px[2 * r] & klo) | (fill & ~klo);
+                            px[2 * r + 1] = (px[2 * r + 1] & khi) | (fill & ~khi);
+                        }
                     }
                 } else {
-                    // clamp-to-edge padding (dbde_util.cpp:105-135), edge tiles only
+                    // the frame's last band when H % 8 != 0: rows past H repeat the last valid row (dbde_util.cpp:111-117)
 #pragma unroll
                     for (int r = 0; r < 8; r++) {
                         uint2 v = load8(addr + (uint32_t)(min(r, rows_valid - 1) * g.W));
@@ -481,9 +569,20 @@ cudaError_t launch_encode(const EncParams &Pin, bool fast, int num_sms, cudaStre
     const bool wide = fast && (P.g.w % kTilesPerPart == 0) && P.g.pitch == kWidePitch;
     const bool contig = !fast && P.g.nseg == 1;
     if (contig) P.g.pitch = P.g.W;        // the stage holds the partition's pixels exactly as they lie in the frame
-    auto kern = wide ? dbde_encode_kernel<true, true, false>
-                     : (fast ? dbde_encode_kernel<true, false, false>
-                             : (contig ? dbde_encode_kernel<false, false, true> : dbde_encode_kernel<false, false, false>));
+    void (*kern)(const EncParams) = nullptr;
+    if (wide) kern = dbde_encode_kernel<true, true, false>;
+    else if (fast) kern = dbde_encode_kernel<true, false, false>;
+    else if (!contig) kern = dbde_encode_kernel<false, false, false>;
+    else switch (P.g.W & 7) {
+        case 0: kern = dbde_encode_kernel<false, false, true, 0>; break;
+        case 1: kern = dbde_encode_kernel<false, false, true, 1>; break;
+        case 2: kern = dbde_encode_kernel<false, false, true, 2>; break;
+        case 3: kern = dbde_encode_kernel<false, false, true, 3>; break;
+        case 4: kern = dbde_encode_kernel<false, false, true, 4>; break;
+        case 5: kern = dbde_encode_kernel<false, false, true, 5>; break;
+        case 6: kern = dbde_encode_kernel<false, false, true, 6>; break;
+        default: kern = dbde_encode_kernel<false, false, true, 7>; break;
+    }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 0;

@@ -132,20 +132,30 @@ def test_sizes_and_edges(codec, W, H):
     roundtrip_check(codec, frames, first_index=1000)
 
 
+@pytest.fixture(params=["direct", "staged"])
+def odd_decode(request, monkeypatch):
+    """both unpack kernels for odd-size frames with full-width partitions: re-aligned row stores straight from
+    registers (the default) and the image staged in shared memory + one bulk store (DBDE_B200_ODD_DECODE=staged)"""
+    monkeypatch.setenv("DBDE_B200_ODD_DECODE", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("W,H", [(1002, 19), (1004, 21), (1006, 17), (1003, 8), (2047, 17), (2041, 33), (2044, 9),
-                                 (5, 1000), (33, 515), (15, 64), (250, 250), (1999, 41)])
-def test_odd_sizes_full_width_partitions(codec, W, H):
-    """W <= 2048 with W % 16 != 0 or H % 8 != 0: the contiguous-hull encoder staging and the staged-store
-    decoder (every row alignment class: W % 8 = 1..7, 2, 4, 6; one to eight bands per partition)"""
+                                 (5, 1000), (33, 515), (15, 64), (250, 250), (1999, 41), (1000, 1003), (257, 64),
+                                 (263, 70), (1016, 30), (2040, 12)])
+def test_odd_sizes_full_width_partitions(codec, odd_decode, W, H):
+    """W <= 2048 with W % 16 != 0 or H % 8 != 0: the contiguous-hull encoder staging and both odd-size
+    decoders (every row alignment class: W % 8 = 0..7; one to eight bands per partition; partial last
+    columns of 1..7 pixels; frames of exactly 32 tiles per band and narrower ones that keep the piecewise stores)"""
     rng = np.random.default_rng(W * 7919 + H)
     frames = np.stack([rand_frame(rng, W, H, ["classes", "noise", "flat", "classes"][i % 4]) for i in range(4)])
     roundtrip_check(codec, frames, first_index=7)
     roundtrip_check(codec, synth.gen_frames("mix", 3, W, H, f0=5))
 
 
-def test_rejected_frames_between_good_ones_odd_size(codec):
-    """the staged-store decoder skips rejected frames without losing step with its store warp
-    (dbde_util.cpp:296-303: image untouched), odd size, several partitions per frame"""
+def test_rejected_frames_between_good_ones_odd_size(codec, odd_decode):
+    """the odd-size decoders skip rejected frames (the staged one without losing step with its store warp;
+    dbde_util.cpp:296-303: image untouched), odd size, several partitions per frame"""
     W, H, N = 1001, 43, 9
     wh = ((W + 7) // 8) * ((H + 7) // 8)
     fr = synth.gen_frames("mix", N, W, H)
@@ -824,8 +834,9 @@ def test_baseline_configs_device_resident_at_scale(codec, kind, N, W, H):
             codec.device_free(p)
 
 
-@pytest.mark.parametrize("W,H,N", [(1001, 1003, 3), (13, 9, 5), (7, 5, 4), (2048, 16, 2), (264, 24, 3), (4100, 12, 2)])
-def test_decoder_and_encoder_never_write_outside_their_buffers(codec, W, H, N):
+@pytest.mark.parametrize("W,H,N", [(1001, 1003, 3), (13, 9, 5), (7, 5, 4), (2048, 16, 2), (264, 24, 3), (4100, 12, 2), (1004, 40, 3),
+                                   (1006, 24, 2), (259, 16, 3)])
+def test_decoder_and_encoder_never_write_outside_their_buffers(codec, odd_decode, W, H, N):
     """guard bytes around the decoder's pixel output and the encoder's slots, at every misalignment of
     the output base: the generic store path assembles aligned 8-byte words across lanes, so a frame's
     first/last bytes share words with the neighbouring memory and must be written with narrow stores"""
