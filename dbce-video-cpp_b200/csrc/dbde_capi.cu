@@ -3,8 +3,10 @@
 // for host buffers.  No codec arithmetic lives here and there is no CPU fallback.
 #include "../../include/dbde_b200.h"
 #include "dbde_kernels.h"
+#include "dbde_copy_pool.h"
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <deque>
@@ -32,6 +34,37 @@ static int cuda_fail(cudaError_t e, const char *where) {
         if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
     } while (0)
 
+// DBDE_B200_PROFILE=1: per-thread wall-clock sums of the host path's phases, printed when the thread ends
+// (where the time of a one-frame call goes: staging copies, launches, waiting for the GPU, copy-out)
+namespace {
+struct PhaseProfile {
+    static bool on() {
+        static const bool v = getenv("DBDE_B200_PROFILE") != nullptr;
+        return v;
+    }
+    const char *name[8] = {};
+    double sum[8] = {};
+    long calls = 0;
+    std::chrono::steady_clock::time_point t;
+    void start() { if (on()) t = std::chrono::steady_clock::now(); }
+    void mark(int i, const char *what) {
+        if (!on()) return;
+        const auto n = std::chrono::steady_clock::now();
+        name[i] = what;
+        sum[i] += std::chrono::duration<double, std::micro>(n - t).count();
+        t = n;
+    }
+    ~PhaseProfile() {
+        if (!on() || !calls) return;
+        std::string line = "dbde_b200 profile (" + std::to_string(calls) + " calls, us per call):";
+        for (int i = 0; i < 8; i++)
+            if (name[i]) line += std::string(" ") + name[i] + "=" + std::to_string((long)(sum[i] / calls));
+        fprintf(stderr, "%s\n", line.c_str());
+    }
+};
+thread_local PhaseProfile g_enc_prof, g_dec_prof;
+}  // namespace
+
 constexpr int kMaxHostSlots = 8;
 constexpr int kDefaultHostSlots = 3;
 
@@ -53,10 +86,13 @@ struct HostSlot {
     // bounce buffers the bytes are relayed through in pieces, by parallel memcpy overlapped with the DMA
     uint8_t *h_in = nullptr, *h_out = nullptr;
     size_t cap_hin = 0, cap_hout = 0;
-    cudaEvent_t pev[16] = {};    // one per piece of a relayed D2H copy
+    // completion flags in pinned memory: a 4-byte D2H copy of the context's device word `1`, queued behind the
+    // work it reports, sets one; host threads wait on them by reading memory, not by calling the driver
+    volatile uint32_t *h_flag = nullptr;    // kMaxDmaPieces for relayed D2H pieces + 1 for the chunk's kernels
     size_t cap_a = 0, cap_b = 0, cap_c = 0;
     int cap_n = 0;
     int n = 0, first = 0;
+    size_t piece = 0;            // DMA piece size of the chunk's relayed pixel copy (decode, pageable output)
 };
 
 // Scan scratch (encode: ticket + look-back descriptors; decode: word prefixes) belongs to the STREAM a
@@ -81,6 +117,7 @@ struct dbde_b200_ctx {
     int chunk_frames = 0;             // frames per chunk, 0 = auto (DBDE_B200_CHUNK_FRAMES)
     int invert_endian = 0;            // DBDE_INVERT_ENDIAN variant; initialised from the process-wide setting
     uint64_t launches = 0;
+    uint32_t *d_one = nullptr;        // a device word holding 1: the source of the completion-flag copies
 };
 
 // ------------------------------------------------------------------ geometry
@@ -197,8 +234,7 @@ static void free_slot(HostSlot &s) {
     if (s.h_index) cudaFreeHost(s.h_index);
     if (s.h_in) cudaFreeHost(s.h_in);
     if (s.h_out) cudaFreeHost(s.h_out);
-    for (auto &e : s.pev)
-        if (e) cudaEventDestroy(e);
+    if (s.h_flag) cudaFreeHost((void *)s.h_flag);
     if (s.ev) cudaEventDestroy(s.ev);
     if (s.st) cudaStreamDestroy(s.st);
     s = HostSlot();
@@ -213,6 +249,7 @@ extern "C" void dbde_b200_destroy(dbde_b200_ctx *c) {
         if (x.enc) cudaFree(x.enc);
         if (x.dec) cudaFree(x.dec);
     }
+    if (c->d_one) cudaFree(c->d_one);
     delete c;
 }
 
@@ -425,93 +462,16 @@ extern "C" int dbde_b200_validate_device(dbde_b200_ctx *c, const uint8_t *stream
 }
 
 // ------------------------------------------------------------------ pageable host memory
-// cudaMemcpyAsync on pageable memory goes through the driver's own staging at ~15 GB/s and blocks the
-// caller; a single host thread's memcpy is no faster (~14 GB/s).  The library therefore relays pageable
-// buffers itself: a small process-wide pool of copy threads moves the bytes between the caller's memory
-// and a pinned bounce buffer in pieces, and each piece's DMA is queued as soon as the piece is there (H2D)
-// / each piece is copied out as soon as its DMA has landed (D2H).  Callers that wait for their pieces
-// execute queued pieces themselves, so many calling threads (one context each) share the pool's work
-// instead of queueing behind it.  Nothing is page-locked behind the caller's back.
+// The reference's callers pass malloc'd buffers (dbde_util.h:24-35).  cudaMemcpyAsync on pageable memory
+// goes through the driver's own staging at ~15 GB/s and blocks the caller, and one host thread's memcpy is
+// no faster (~14 GB/s).  The library therefore relays pageable buffers itself through pinned bounce
+// buffers: the bytes are cut into 256 KiB copy jobs that a small process-wide pool of copy threads AND
+// every calling thread that is waiting for something execute, each stretch of finished pieces is sent with
+// one DMA (H2D) / each DMA piece is copied out as soon as it has landed (D2H).  Every wait on this path --
+// for one's own pieces, for a kernel, for a DMA -- is a helping wait: the waiting thread runs queued jobs
+// (anyone's), so sixteen callers share the copying among themselves instead of spinning in the driver while
+// the threads that hold their data are descheduled.  Nothing is page-locked behind the caller's back.
 namespace {
-class CopyPool {
-  public:
-    struct Job {
-        uint8_t *dst;
-        const uint8_t *src;
-        size_t n;
-        std::atomic<int> *pending;
-    };
-    static CopyPool &get() {
-        static CopyPool p;
-        return p;
-    }
-    void submit(uint8_t *dst, const uint8_t *src, size_t n, std::atomic<int> *pending) {
-        pending->fetch_add(1, std::memory_order_relaxed);
-        {
-            std::lock_guard<std::mutex> lk(m_);
-            q_.push_back(Job{dst, src, n, pending});
-        }
-        queued_.fetch_add(1, std::memory_order_release);
-        cv_.notify_one();
-    }
-    bool run_one() {
-        if (queued_.load(std::memory_order_acquire) <= 0) return false;
-        Job j;
-        {
-            std::lock_guard<std::mutex> lk(m_);
-            if (q_.empty()) return false;
-            j = q_.front();
-            q_.pop_front();
-        }
-        queued_.fetch_sub(1, std::memory_order_relaxed);
-        memcpy(j.dst, j.src, j.n);
-        j.pending->fetch_sub(1, std::memory_order_release);
-        return true;
-    }
-    // wait until the jobs counted by `pending` are done, copying queued pieces (anyone's) meanwhile
-    void wait(std::atomic<int> &pending) {
-        while (pending.load(std::memory_order_acquire) > 0)
-            if (!run_one()) __builtin_ia32_pause();
-    }
-
-  private:
-    CopyPool() {
-        int n = (int)std::thread::hardware_concurrency() / 2;
-        if (n > 6) n = 6;
-        if (const char *e = getenv("DBDE_B200_COPY_THREADS")) n = atoi(e);
-        if (n < 0) n = 0;
-        for (int i = 0; i < n; i++) th_.emplace_back([this] { work(); });
-    }
-    ~CopyPool() {
-        {
-            std::lock_guard<std::mutex> lk(m_);
-            stop_ = true;
-        }
-        cv_.notify_all();
-        for (auto &t : th_) t.join();
-    }
-    void work() {
-        for (;;) {
-            // a caller in a loop finds the threads still spinning; an idle process finds them asleep
-            bool did = false;
-            for (int spin = 0; spin < 4000; spin++) {
-                if (run_one()) { did = true; break; }
-                __builtin_ia32_pause();
-            }
-            if (did) continue;
-            std::unique_lock<std::mutex> lk(m_);
-            cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
-            if (stop_) return;
-        }
-    }
-    std::mutex m_;
-    std::condition_variable cv_;
-    std::deque<Job> q_;
-    std::atomic<int> queued_{0};
-    std::vector<std::thread> th_;
-    bool stop_ = false;
-};
-
 bool is_pageable(const void *p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -521,15 +481,23 @@ bool is_pageable(const void *p) {
     return a.type == cudaMemoryTypeUnregistered;
 }
 
-constexpr int kRelayPieces = 16;
-size_t relay_piece(size_t n) {
-    size_t piece = (n + kRelayPieces - 1) / kRelayPieces;
-    if (piece < (256u << 10)) piece = 256u << 10;
-    return (piece + 4095) & ~(size_t)4095;
+constexpr size_t kCopyJobBytes = 256u << 10;      // one memcpy job
+constexpr int kMaxCopyJobs = 64;                  // per relayed buffer (larger buffers use larger jobs)
+constexpr int kMaxDmaPieces = 16;                 // D2H pieces per relayed buffer (one event each)
+size_t copy_job_bytes(size_t n) {
+    size_t job = kCopyJobBytes;
+    while ((n + job - 1) / job > (size_t)kMaxCopyJobs) job *= 2;
+    return job;
+}
+constexpr int kFlagKernels = kMaxDmaPieces;       // index of the "this chunk's kernels are done" flag
+// wait for a completion flag, copying queued pieces meanwhile
+void wait_flag_helping(volatile uint32_t *flag) {
+    CopyPool::get().help_until([flag] { return *flag != 0u; });
+    std::atomic_thread_fence(std::memory_order_acquire);       // the bytes the flag reports are read after it
 }
 }  // namespace
 
-static int ensure_bounce(HostSlot &s, size_t need_in, size_t need_out) {
+static int ensure_bounce(dbde_b200_ctx *c, HostSlot &s, size_t need_in, size_t need_out) {
     if (need_in && s.cap_hin < need_in) {
         if (s.h_in) CK(cudaFreeHost(s.h_in));
         s.h_in = nullptr;
@@ -542,48 +510,104 @@ static int ensure_bounce(HostSlot &s, size_t need_in, size_t need_out) {
         CK(cudaHostAlloc(&s.h_out, need_out, cudaHostAllocDefault));
         s.cap_hout = need_out;
     }
-    if (need_out && !s.pev[0])
-        for (auto &e : s.pev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (!s.h_flag) {
+        void *p = nullptr;
+        CK(cudaHostAlloc(&p, 4 * (kMaxDmaPieces + 1), cudaHostAllocDefault));
+        memset(p, 0, 4 * (kMaxDmaPieces + 1));
+        s.h_flag = (volatile uint32_t *)p;
+    }
+    if (!c->d_one) {
+        const uint32_t one = 1;
+        CK(cudaMalloc(&c->d_one, 4));
+        CK(cudaMemcpy(c->d_one, &one, 4, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+// queue "set flag i" behind everything already on the slot's stream
+static int signal_flag(dbde_b200_ctx *c, HostSlot &s, int i) {
+    s.h_flag[i] = 0u;
+    CK(cudaMemcpyAsync((void *)&s.h_flag[i], c->d_one, 4, cudaMemcpyDeviceToHost, s.st));
     return 0;
 }
 
 // pageable src -> device, through the slot's pinned h_in (at offset hoff), queued on the slot's stream.
 // Returns when every piece's DMA is queued; the bounce bytes stay valid until the stream has passed them.
+// Copy jobs are 256 KiB (many hands), DMAs at least 1 MiB (a DMA costs microseconds to start).
 static int relay_h2d(HostSlot &s, uint8_t *d_dst, const uint8_t *src, size_t n, size_t hoff) {
+    if (!n) return 0;
     CopyPool &pool = CopyPool::get();
-    const size_t piece = relay_piece(n);
-    std::atomic<int> pend[kRelayPieces];
-    int np = 0;
-    for (size_t o = 0; o < n; o += piece, np++) {
-        pend[np].store(0, std::memory_order_relaxed);
-        pool.submit(s.h_in + hoff + o, src + o, n - o < piece ? n - o : piece, &pend[np]);
+    const size_t job = copy_job_bytes(n);
+    const int nj = (int)((n + job - 1) / job);
+    std::atomic<int> pend[kMaxCopyJobs];
+    CopyPool::Job jobs[kMaxCopyJobs];
+    for (int i = 0; i < nj; i++) {
+        const size_t o = (size_t)i * job;
+        pend[i].store(1, std::memory_order_relaxed);
+        jobs[i] = CopyPool::Job{s.h_in + hoff + o, src + o, n - o < job ? n - o : job, &pend[i]};
     }
-    int j = 0;
-    for (size_t o = 0; o < n; o += piece, j++) {
-        pool.wait(pend[j]);
-        CK(cudaMemcpyAsync(d_dst + o, s.h_in + hoff + o, n - o < piece ? n - o : piece, cudaMemcpyHostToDevice, s.st));
+    pool.submit(jobs, nj);
+    static const size_t dma_min = [] {
+        const char *e = getenv("DBDE_B200_H2D_DMA_KB");
+        return (size_t)(e && atoi(e) > 0 ? atoi(e) : 1024) << 10;
+    }();
+    const int group = (int)((dma_min + job - 1) / job);      // jobs per DMA
+    for (int i = 0; i < nj;) {
+        int j = i + group < nj ? i + group : nj;
+        for (int q = i; q < j; q++) pool.help_until([&] { return pend[q].load(std::memory_order_acquire) == 0; });
+        while (j < nj && pend[j].load(std::memory_order_acquire) == 0) j++;      // whatever else is already there
+        const size_t o0 = (size_t)i * job, o1 = j < nj ? (size_t)j * job : n;
+        CK(cudaMemcpyAsync(d_dst + o0, s.h_in + hoff + o0, o1 - o0, cudaMemcpyHostToDevice, s.st));
+        i = j;
     }
     return 0;
 }
 
-// device -> pageable dst, through the slot's pinned h_out (at offset hoff).  Synchronous: the bytes are in
-// dst on return.  Pieces are copied out by the pool while later pieces are still crossing PCIe.
-static int relay_d2h(HostSlot &s, uint8_t *dst, const uint8_t *d_src, size_t n, size_t hoff) {
-    if (!n) return 0;
-    CopyPool &pool = CopyPool::get();
-    const size_t piece = relay_piece(n);
-    int np = 0;
-    for (size_t o = 0; o < n; o += piece, np++) {
+// device -> the slot's pinned h_out (at offset hoff), in DMA pieces with one completion flag each, queued on
+// the slot's stream.  Returns the piece size; pieces k = 0 .. ceil(n / piece) - 1 report on h_flag[k].
+static int relay_d2h_enqueue(dbde_b200_ctx *c, HostSlot &s, const uint8_t *d_src, size_t n, size_t hoff, size_t *piece_out) {
+    static const size_t piece_min = [] {
+        const char *e = getenv("DBDE_B200_D2H_DMA_KB");
+        return (size_t)(e && atoi(e) > 0 ? atoi(e) : 1024) << 10;
+    }();
+    size_t piece = piece_min;
+    while ((n + piece - 1) / piece > (size_t)kMaxDmaPieces) piece *= 2;
+    const int np = (int)((n + piece - 1) / piece);
+    for (int k = 0; k < np; k++) {
+        const size_t o = (size_t)k * piece;
         CK(cudaMemcpyAsync(s.h_out + hoff + o, d_src + o, n - o < piece ? n - o : piece, cudaMemcpyDeviceToHost, s.st));
-        CK(cudaEventRecord(s.pev[np], s.st));
+        int rc = signal_flag(c, s, k);
+        if (rc) return rc;
     }
+    *piece_out = piece;
+    return 0;
+}
+// ... and out of h_out into pageable memory as the pieces land: bytes [lo, hi) of the n relayed bytes go to
+// dst + (their offset - lo).  Pieces are copied out by the pool and the waiting callers while later pieces
+// are still crossing PCIe; `pend` counts the jobs (the caller waits for it once, after its last range).
+static void relay_d2h_collect(HostSlot &s, uint8_t *dst, size_t lo, size_t hi, size_t n, size_t piece, size_t hoff,
+                              std::atomic<int> &pend) {
+    CopyPool &pool = CopyPool::get();
+    const size_t job = copy_job_bytes(piece);
+    for (size_t k = lo / piece; k * piece < hi && k * piece < n; k++) {
+        wait_flag_helping(&s.h_flag[k]);
+        const size_t p0 = k * piece > lo ? k * piece : lo, p1 = (k + 1) * piece < hi ? (k + 1) * piece : hi;
+        CopyPool::Job jobs[kMaxCopyJobs + 1];
+        int nj = 0;
+        for (size_t q = p0; q < p1; q += job) jobs[nj++] = CopyPool::Job{dst + (q - lo), s.h_out + hoff + q, p1 - q < job ? p1 - q : job, &pend};
+        pend.fetch_add(nj, std::memory_order_relaxed);
+        pool.submit(jobs, nj);
+    }
+}
+// device -> pageable dst.  Synchronous: the bytes are in dst on return.
+static int relay_d2h(dbde_b200_ctx *c, HostSlot &s, uint8_t *dst, const uint8_t *d_src, size_t n, size_t hoff) {
+    if (!n) return 0;
+    size_t piece = 0;
+    int rc = relay_d2h_enqueue(c, s, d_src, n, hoff, &piece);
+    if (rc) return rc;
     std::atomic<int> pend{0};
-    int j = 0;
-    for (size_t o = 0; o < n; o += piece, j++) {
-        CK(cudaEventSynchronize(s.pev[j]));
-        pool.submit(dst + o, s.h_out + hoff + o, n - o < piece ? n - o : piece, &pend);
-    }
-    pool.wait(pend);
+    relay_d2h_collect(s, dst, 0, n, n, piece, hoff, pend);
+    CopyPool::get().help_until([&] { return pend.load(std::memory_order_acquire) == 0; });
     return 0;
 }
 
@@ -668,7 +692,7 @@ static int encode_host_worker(dbde_b200_ctx *c, const uint8_t *frames_host, int 
     const bool in_pageable = is_pageable(frames_host), out_pageable = is_pageable(out_host);
     for (int i = 0; i < ns; i++) {
         int rc = ensure_slot(c, c->slots[i], need_a, need_b, chunk > 1 ? need_b : 0, chunk);
-        if (!rc) rc = ensure_bounce(c->slots[i], in_pageable ? px * chunk : 0, out_pageable ? need_b : 0);
+        if (!rc) rc = ensure_bounce(c, c->slots[i], in_pageable ? px * chunk : 0, out_pageable ? need_b : 0);
         if (rc) return rc;
     }
     const size_t stride = dbde_b200_slot_stride(W, H);
@@ -678,7 +702,9 @@ static int encode_host_worker(dbde_b200_ctx *c, const uint8_t *frames_host, int 
     auto finish = [&](int li) -> int {
         HostSlot &s = c->slots[li % ns];
         const int ci = my + li * nworkers;
-        CK(cudaEventSynchronize(s.ev));
+        if (in_pageable || out_pageable) wait_flag_helping(&s.h_flag[kFlagKernels]);    // copy (anyone's pieces) while waiting
+        else CK(cudaEventSynchronize(s.ev));
+        g_enc_prof.mark(3, "gpu");
         uint64_t total = 0;
         for (int i = 0; i < s.n; i++) total += s.h_size[i];
         while (seq->next.load(std::memory_order_acquire) != ci) {
@@ -695,15 +721,23 @@ static int encode_host_worker(dbde_b200_ctx *c, const uint8_t *frames_host, int 
             run += s.h_size[i];
         }
         const uint8_t *d_rec = chunk > 1 ? s.d_c : s.d_b + delta;
-        if (out_pageable) return relay_d2h(s, out_host + pos, d_rec, total, 0);
+        if (out_pageable) {
+            const int rc = relay_d2h(c, s, out_host + pos, d_rec, total, 0);
+            g_enc_prof.mark(4, "d2h");
+            return rc;
+        }
         CK(cudaMemcpyAsync(out_host + pos, d_rec, total, cudaMemcpyDeviceToHost, s.st));
         return 0;
     };
     int pending = -1, rc_all = 0;
+    PhaseProfile &prof = g_enc_prof;
+    prof.calls++;
+    prof.start();
     for (int li = 0; li < mine && !rc_all; li++) {
         HostSlot &s = c->slots[li % ns];
         const int ci = my + li * nworkers;
         CK(cudaStreamSynchronize(s.st));            // the slot's previous chunk has fully drained
+        prof.mark(0, "setup");
         s.first = ci * chunk;
         s.n = nframes - s.first < chunk ? nframes - s.first : chunk;
         if (in_pageable) {
@@ -712,6 +746,7 @@ static int encode_host_worker(dbde_b200_ctx *c, const uint8_t *frames_host, int 
         } else {
             CK(cudaMemcpyAsync(s.d_a, frames_host + px * s.first, px * s.n, cudaMemcpyHostToDevice, s.st));
         }
+        prof.mark(1, "h2d");
         rc_all = dbde_b200_encode_device(c, s.d_a, W, H, first_index + s.first, s.n, s.d_b + delta, need_b - 32, stride,
                                          s.d_off, s.d_size, s.st);
         if (rc_all) break;
@@ -720,13 +755,20 @@ static int encode_host_worker(dbde_b200_ctx *c, const uint8_t *frames_host, int 
             CK(launch_compact(s.d_b + delta, stride, s.d_size, s.n, s.d_c, s.st));
             c->launches += 1;
         }
-        CK(cudaEventRecord(s.ev, s.st));
+        if (in_pageable || out_pageable) {
+            rc_all = signal_flag(c, s, kFlagKernels);
+            if (rc_all) break;
+        } else {
+            CK(cudaEventRecord(s.ev, s.st));
+        }
+        prof.mark(2, "launch");
         if (pending >= 0) rc_all = finish(pending);
         pending = li;
     }
     if (!rc_all && pending >= 0) rc_all = finish(pending);
     for (auto &s : c->slots)
         if (s.st) cudaStreamSynchronize(s.st);
+    prof.mark(5, "drain");
     return rc_all;
 }
 
@@ -783,7 +825,7 @@ static int decode_host_impl(dbde_b200_ctx *c, const uint8_t *stream_host, size_t
     const bool in_pageable = is_pageable(stream_host), out_pageable = !scan_only && is_pageable(frames_host);
     for (int i = 0; i < ns; i++) {
         int rc = ensure_slot(c, c->slots[i], need_a, need_b, 0, chunk);
-        if (!rc) rc = ensure_bounce(c->slots[i], in_pageable ? need_a : 0, out_pageable ? px * chunk : 0);
+        if (!rc) rc = ensure_bounce(c, c->slots[i], in_pageable ? need_a : 0, out_pageable ? px * chunk : 0);
         if (rc) return rc;
     }
     // finish(): wait for a chunk's status words, then queue the D2H of its accepted frames.  A
@@ -791,10 +833,15 @@ static int decode_host_impl(dbde_b200_ctx *c, const uint8_t *stream_host, size_t
     // come back as maximal runs of accepted frames.
     auto finish = [&](int ci) -> int {
         HostSlot &s = c->slots[ci % ns];
-        CK(cudaEventSynchronize(s.ev));
+        if (in_pageable || out_pageable) wait_flag_helping(&s.h_flag[kFlagKernels]);
+        else CK(cudaEventSynchronize(s.ev));
+        g_dec_prof.mark(3, "gpu");
         memcpy(status_host + s.first, s.h_status, 4 * (size_t)s.n);
         if (indices_host) memcpy(indices_host + s.first, s.h_index, 8 * (size_t)s.n);
         if (scan_only) return 0;
+        // pageable output: the chunk's pixels are already on their way to the bounce buffer (queued right
+        // behind the kernels, before the status words were known); only accepted frames leave it
+        std::atomic<int> pend{0};
         int run0 = 0;
         for (int i = 0; i <= s.n; i++) {
             const bool ok = i < s.n && s.h_status[i] == 0;
@@ -802,8 +849,7 @@ static int decode_host_impl(dbde_b200_ctx *c, const uint8_t *stream_host, size_t
                 if (i > run0) {
                     const size_t bytes = px * (size_t)(i - run0);
                     if (out_pageable) {
-                        int rc = relay_d2h(s, frames_host + px * (s.first + run0), s.d_b + px * run0, bytes, px * run0);
-                        if (rc) return rc;
+                        relay_d2h_collect(s, frames_host + px * (s.first + run0), px * run0, px * run0 + bytes, px * s.n, s.piece, 0, pend);
                     } else {
                         CK(cudaMemcpyAsync(frames_host + px * (s.first + run0), s.d_b + px * run0, bytes, cudaMemcpyDeviceToHost, s.st));
                     }
@@ -811,12 +857,18 @@ static int decode_host_impl(dbde_b200_ctx *c, const uint8_t *stream_host, size_t
                 run0 = i + 1;
             }
         }
+        if (out_pageable) CopyPool::get().help_until([&] { return pend.load(std::memory_order_acquire) == 0; });
+        g_dec_prof.mark(4, "d2h");
         return 0;
     };
     int pending = -1, rc_all = 0;
+    PhaseProfile &prof = g_dec_prof;
+    prof.calls++;
+    prof.start();
     for (int ci = 0; ci < nchunks && !rc_all; ci++) {
         HostSlot &s = c->slots[ci % ns];
         CK(cudaStreamSynchronize(s.st));
+        prof.mark(0, "setup");
         s.first = ci * chunk;
         s.n = nframes - s.first < chunk ? nframes - s.first : chunk;
         const uint64_t b0 = frame_offsets_host[s.first];
@@ -829,18 +881,27 @@ static int decode_host_impl(dbde_b200_ctx *c, const uint8_t *stream_host, size_t
         } else {
             CK(cudaMemcpyAsync(s.d_a + delta, stream_host + b0, b1 - b0, cudaMemcpyHostToDevice, s.st));
         }
+        prof.mark(1, "h2d");
         rc_all = decode_device_impl(c, s.d_a + delta, b1 - b0, s.d_off, W, H, s.n, s.d_b, s.d_status, s.d_index, s.st,
                                     scan_only);
         if (rc_all) break;
         CK(cudaMemcpyAsync(s.h_status, s.d_status, 4 * (size_t)s.n, cudaMemcpyDeviceToHost, s.st));
         if (indices_host) CK(cudaMemcpyAsync(s.h_index, s.d_index, 8 * (size_t)s.n, cudaMemcpyDeviceToHost, s.st));
-        CK(cudaEventRecord(s.ev, s.st));
+        if (in_pageable || out_pageable) {
+            rc_all = signal_flag(c, s, kFlagKernels);
+            if (!rc_all && out_pageable && !scan_only) rc_all = relay_d2h_enqueue(c, s, s.d_b, px * (size_t)s.n, 0, &s.piece);
+            if (rc_all) break;
+        } else {
+            CK(cudaEventRecord(s.ev, s.st));
+        }
+        prof.mark(2, "launch");
         if (pending >= 0) rc_all = finish(pending);
         pending = ci;
     }
     if (!rc_all && pending >= 0) rc_all = finish(pending);
     for (auto &s : c->slots)
         if (s.st) cudaStreamSynchronize(s.st);
+    prof.mark(5, "drain");
     return rc_all;
 }
 

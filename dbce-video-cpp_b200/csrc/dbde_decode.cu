@@ -301,24 +301,12 @@ __device__ __forceinline__ void store_row_generic(uint8_t *rp, uint64_t x, int n
 //   a in 5..7   : word at T + 8 - a = [my last a bytes | right neighbour's first 8 - a] (needs the neighbour's low half)
 // With W & 7 a template parameter and the partition's first alignment a switch case, every row's
 // shape and shift amount is a compile-time constant.  What the words cannot cover -- the first 8 - a
-// bytes of a run's first lane and the last a bytes of its last lane, per row -- is written once per
-// partition by a boundary pass: the end lanes leave their pixels in a 256-byte scratch of their warp,
-// and lane (run, row, end) stores that piece as at most three naturally aligned narrow stores.
-#ifndef DBDE_DIR_ROWENDS
-#define DBDE_DIR_ROWENDS 1       // run ends stored row by row with compile-time shapes (0: per-partition boundary pass)
-#endif
-#ifndef DBDE_DEC_DIRECT_CS
-#define DBDE_DEC_DIRECT_CS 0     // 1: streaming (evict-first) policy for the re-aligned word stores
-#endif
-#ifndef DBDE_DEC_DIRECT_MINB
-#define DBDE_DEC_DIRECT_MINB 4   // resident CTAs per SM the odd-size kernel is compiled for (register cap 56 at 4)
-#endif
+// bytes of a run's first lane and the last a bytes of its last lane -- those two lanes store as at most
+// three naturally aligned narrow pieces per row, also of compile-time shape (store_row_ends).
+// (Measured alternative: the end lanes leave their pixels in a per-warp scratch and a per-partition
+// boundary pass -- lane = (run, row, end) -- writes the pieces: 12 % slower, mix-1001x1003 3.57 vs 4.05 TB/s.)
 __device__ __forceinline__ void stg_u64(uint8_t *p, uint32_t lo, uint32_t hi) {
-#if DBDE_DEC_DIRECT_CS
-    asm volatile("st.global.cs.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(lo), "r"(hi) : "memory");
-#else
     asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(lo), "r"(hi) : "memory");
-#endif
 }
 __device__ __forceinline__ void stg_u32(uint8_t *p, uint32_t v) { asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void stg_u16(uint8_t *p, uint32_t v) {
@@ -326,40 +314,19 @@ __device__ __forceinline__ void stg_u16(uint8_t *p, uint32_t v) {
 }
 __device__ __forceinline__ void stg_u8(uint8_t *p, uint32_t v) { asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-constexpr int kDirScratchPerWarp = 256;      // 4 end lanes x 64 pixel bytes
 constexpr uint32_t kDirFull = 1, kDirFirst = 2, kDirLast = 4, kDirPartial = 8;
-struct DirectLane {
-    uint32_t flags;      // kDir* | ncol << 8 | scratch slot of this lane's pixels as a run's first lane << 16 (15 = none)
-                         // | the same as a run's last lane << 20
-    uint32_t item;       // my boundary piece: bit 0 valid, bit 1 end (0 head, 1 tail), bits 4-6 row, bits 8-9 scratch slot,
-                         // bits 16.. tid of the lane whose piece it is
-    uint32_t item_toff;  // that lane's tile offset inside the partition's pixels
-};
-// Who is where in this warp: runs of full-width tiles of one band (at most two per warp when the frame is
-// at least 32 tiles wide), the partial last column, and which boundary piece this lane will write.
-// Warp-wide call (ballots, shuffle).  tx0/ntx: the partition's first tile column and tile columns.
-__device__ __forceinline__ DirectLane direct_setup(const PartGeom &g, int tid, int lane, int stx, uint32_t toff, int tx0,
-                                                   int ntx, int tiles_max) {
-    DirectLane d;
+// Where this lane's tile sits in its image row: kDirFull (all 8 columns inside the frame), kDirFirst / kDirLast
+// (no full tile of the same band in the lane to the left / right: a run of re-aligned words starts / ends
+// here), kDirPartial (the frame's last column when W % 8 != 0) | its column count << 8.
+// tx0/ntx: the partition's first tile column and tile columns; tiles_max: tiles a partition can hold.
+__device__ __forceinline__ uint32_t direct_lane_flags(const PartGeom &g, int tid, int lane, int stx, int tx0, int ntx, int tiles_max) {
     const bool ingeo = tid < tiles_max;
     const int ncol = ingeo ? min(8, g.W - 8 * (tx0 + stx)) : 0;       // lanes past the partition's tiles: nothing
     const bool full = ingeo && ncol == 8;
     const bool left_full = lane > 0 && stx > 0;                                           // only a last column can be partial
     const bool right_full = lane < 31 && stx + 1 < ntx && g.W - 8 * (tx0 + stx + 1) >= 8;
-    const bool first = full && !left_full, last = full && !right_full;
-    d.flags = (full ? kDirFull : 0u) | (first ? kDirFirst : 0u) | (last ? kDirLast : 0u) | (ingeo && ncol < 8 ? kDirPartial : 0u) |
-              ((uint32_t)ncol << 8);
-    const uint32_t mf = __ballot_sync(0xffffffffu, first), ml = __ballot_sync(0xffffffffu, last);
-    const uint32_t below = (1u << lane) - 1u;
-    d.flags |= ((first ? (uint32_t)__popc(mf & below) : 15u) << 16) | ((last ? 2u + (uint32_t)__popc(ml & below) : 15u) << 20);
-    const int run = lane >> 4, r = (lane >> 1) & 7, e = lane & 1;
-    const uint32_t m = e ? ml : mf;
-    const uint32_t m1 = run ? (m & (m - 1u)) : m;                                         // drop the first run's lane
-    const int src = m1 ? __ffs((int)m1) - 1 : 0;
-    d.item = (m1 ? 1u : 0u) | ((uint32_t)e << 1) | ((uint32_t)r << 4) | ((uint32_t)(2 * e + run) << 8) |
-             ((uint32_t)(tid - lane + src) << 16);
-    d.item_toff = __shfl_sync(0xffffffffu, toff, src);
-    return d;
+    return (full ? kDirFull : 0u) | (full && !left_full ? kDirFirst : 0u) | (full && !right_full ? kDirLast : 0u) |
+           (ingeo && ncol < 8 ? kDirPartial : 0u) | ((uint32_t)ncol << 8);
 }
 
 // bytes [O, O + 4) of the 8-byte row {lo, hi}, O a compile-time constant (zero-filled past byte 7)
@@ -390,8 +357,7 @@ __device__ __forceinline__ void store_row_ends(uint8_t *rp, uint32_t lo, uint32_
 }
 
 // the eight rows of every lane's tile, alignment of row 0 = A0, frame width & 7 = WM.  Warp-wide call.
-// ENDS: the run ends' leftover pieces are stored here, row by row (else by the per-partition boundary pass).
-template <int WM, int A0, bool ENDS, int R>
+template <int WM, int A0, int R>
 __device__ __forceinline__ void store_rows_direct_from(uint8_t *rp, size_t W, const uint32_t (&px)[16], bool full, bool has_left,
                                                        bool has_right, bool efirst, bool elast) {
     if constexpr (R < 8) {
@@ -409,40 +375,28 @@ __device__ __forceinline__ void store_rows_direct_from(uint8_t *rp, size_t W, co
             const uint32_t w0 = __funnelshift_r(lo, hi, 8 * (8 - a)), w1 = __funnelshift_r(hi, nl, 8 * (8 - a));
             if (has_right) stg_u64(rp + (8 - a), w0, w1);
         }
-        if constexpr (ENDS && a != 0) store_row_ends<a>(rp, lo, hi, efirst, elast);
-        store_rows_direct_from<WM, A0, ENDS, R + 1>(rp + W, W, px, full, has_left, has_right, efirst, elast);
+        if constexpr (a != 0) store_row_ends<a>(rp, lo, hi, efirst, elast);
+        store_rows_direct_from<WM, A0, R + 1>(rp + W, W, px, full, has_left, has_right, efirst, elast);
     }
 }
-template <int WM, int A0, bool ENDS>
+template <int WM, int A0>
 __device__ __forceinline__ void store_rows_direct(uint8_t *rp, size_t W, const uint32_t (&px)[16], bool full, bool first,
                                                   bool last) {
-    store_rows_direct_from<WM, A0, ENDS, 0>(rp, W, px, full, full && !first, full && !last, full && first, full && last);
+    store_rows_direct_from<WM, A0, 0>(rp, W, px, full, full && !first, full && !last, full && first, full && last);
 }
-template <int WM, bool ENDS>
+template <int WM>
 __device__ __forceinline__ void store_rows_direct_any(uint32_t a0, uint8_t *rp, size_t W, const uint32_t (&px)[16], bool full,
                                                       bool first, bool last) {
     switch (a0 & 7u) {
-        case 0: store_rows_direct<WM, 0, ENDS>(rp, W, px, full, first, last); break;
-        case 1: store_rows_direct<WM, 1, ENDS>(rp, W, px, full, first, last); break;
-        case 2: store_rows_direct<WM, 2, ENDS>(rp, W, px, full, first, last); break;
-        case 3: store_rows_direct<WM, 3, ENDS>(rp, W, px, full, first, last); break;
-        case 4: store_rows_direct<WM, 4, ENDS>(rp, W, px, full, first, last); break;
-        case 5: store_rows_direct<WM, 5, ENDS>(rp, W, px, full, first, last); break;
-        case 6: store_rows_direct<WM, 6, ENDS>(rp, W, px, full, first, last); break;
-        default: store_rows_direct<WM, 7, ENDS>(rp, W, px, full, first, last); break;
+        case 0: store_rows_direct<WM, 0>(rp, W, px, full, first, last); break;
+        case 1: store_rows_direct<WM, 1>(rp, W, px, full, first, last); break;
+        case 2: store_rows_direct<WM, 2>(rp, W, px, full, first, last); break;
+        case 3: store_rows_direct<WM, 3>(rp, W, px, full, first, last); break;
+        case 4: store_rows_direct<WM, 4>(rp, W, px, full, first, last); break;
+        case 5: store_rows_direct<WM, 5>(rp, W, px, full, first, last); break;
+        case 6: store_rows_direct<WM, 6>(rp, W, px, full, first, last); break;
+        default: store_rows_direct<WM, 7>(rp, W, px, full, first, last); break;
     }
-}
-
-// One boundary piece: bytes [0, 8 - a) of a run's first lane (head, at T) or bytes [8 - a, 8) of its last
-// lane (tail, at T + 8 - a), x = that lane's row.  Sizes 1/2/4 in the order that keeps every store
-// naturally aligned: ascending from T for a head, descending from the 8-byte boundary for a tail.
-__device__ __forceinline__ void store_boundary_piece(uint8_t *T, uint2 x, uint32_t a, uint32_t e) {
-    const uint32_t n = e ? a : 8u - a, s = e ? 8u - a : 0u;
-    const uint32_t o8 = s + (e ? (n & 6u) : 0u), o16 = s + (e ? (n & 4u) : (n & 1u)), o32 = s + (e ? 0u : (n & 3u));
-    auto at = [&](uint32_t o) { return __funnelshift_r((o & 4u) ? x.y : x.x, (o & 4u) ? 0u : x.y, 8u * (o & 3u)); };
-    if (n & 1u) stg_u8(T + o8, at(o8));
-    if (n & 2u) stg_u16(T + o16, at(o16));
-    if (n & 4u) stg_u32(T + o32, at(o32));
 }
 
 // ------------------------------------------------------------------ one lane == one tile: payload -> pixels
@@ -579,10 +533,10 @@ __device__ __forceinline__ void dec_producer(const DecParams &P, DecSmemT<NSTAGE
 }
 
 // MODE -1: aligned frames (W % 16 == 0, H % 8 == 0, 16-byte aligned base): rows are stored as they are.
-// MODE 0..7 = W & 7: every other geometry; rows are re-aligned across lanes (store_rows_direct) when the
-//           frame is at least 32 tiles wide and the partition has no cropped rows, else stored piecewise.
+// MODE 0..7 = W & 7: every other geometry; rows are re-aligned across lanes (store_rows_direct) unless the
+//           partition has cropped rows (the frame's last band when H % 8 != 0), which are stored piecewise.
 template <int MODE>
-__global__ void __launch_bounds__(kDecThreads, MODE < 0 ? 3 : DBDE_DEC_DIRECT_MINB) dbde_decode_kernel(const DecParams P) {
+__global__ void __launch_bounds__(kDecThreads, MODE < 0 ? 3 : 4) dbde_decode_kernel(const DecParams P) {
     constexpr bool FAST = MODE < 0;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     DecSmem &S = *reinterpret_cast<DecSmem *>(smem_raw);
@@ -611,13 +565,10 @@ __global__ void __launch_bounds__(kDecThreads, MODE < 0 ? 3 : DBDE_DEC_DIRECT_MI
         }
         const uint32_t toff = (uint32_t)(8 * sb) * (uint32_t)g.W + 8u * (uint32_t)stx;   // my tile inside a partition's pixels
         const size_t rowstride = (size_t)g.W;
-        // direct re-aligned stores: the warp's run structure is fixed for full-width partitions and is
+        // direct re-aligned stores: a lane's place in its image row is fixed for full-width partitions and is
         // worked out per partition for band segments of wider frames (the last segment is shorter)
-        const bool direct_geom = !FAST && g.w >= 32;
-        DirectLane dl = {0u, 0u, 0u};
-        if (direct_geom && g.nseg == 1) dl = direct_setup(g, tid, lane, stx, toff, 0, g.w, g.G * g.w);
-        uint8_t *scr = stages + (size_t)kDecStages * kDecStageBytes + (size_t)warp * kDirScratchPerWarp;
-        (void)scr;
+        uint32_t dflags = 0;
+        if (!FAST && g.nseg == 1) dflags = direct_lane_flags(g, tid, lane, stx, 0, g.w, g.G * g.w);
         for (unsigned it = 0;; it++) {
             const int s = it % kDecStages;
             const uint32_t ph = (it / kDecStages) & 1;
@@ -651,34 +602,13 @@ __global__ void __launch_bounds__(kDecThreads, MODE < 0 ? 3 : DBDE_DEC_DIRECT_MI
                         rp += rowstride;
                     }
                 }
-            } else if (direct_geom && (c0.y & kCtlAllRows)) {
-                if (g.nseg > 1) dl = direct_setup(g, tid, lane, stx, toff, c2.y, c2.z, c2.z);
-                const bool full = valid && (dl.flags & kDirFull);
-#if DBDE_DIR_ROWENDS
-                store_rows_direct_any<(MODE < 0 ? 0 : MODE), true>((uint32_t)c2.w, rp, rowstride, px, full, (dl.flags & kDirFirst) != 0,
-                                                                   (dl.flags & kDirLast) != 0);
-#else
-                // the end lanes of every run leave their pixels where the boundary pass finds them
-                {
-                    const uint32_t df = (dl.flags >> 16) & 15u, dt = (dl.flags >> 20) & 15u;
-                    if (df != 15u) {
-#pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            *reinterpret_cast<uint4 *>(scr + 64 * df + 16 * j) = make_uint4(px[4 * j], px[4 * j + 1], px[4 * j + 2], px[4 * j + 3]);
-                    }
-                    if (dt != 15u) {
-#pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            *reinterpret_cast<uint4 *>(scr + 64 * dt + 16 * j) = make_uint4(px[4 * j], px[4 * j + 1], px[4 * j + 2], px[4 * j + 3]);
-                    }
-                }
-                __syncwarp();
-                store_rows_direct_any<(MODE < 0 ? 0 : MODE), false>((uint32_t)c2.w, rp, rowstride, px, full, (dl.flags & kDirFirst) != 0,
-                                                                    (dl.flags & kDirLast) != 0);
-#endif
-                if (valid && (dl.flags & kDirPartial)) {
+            } else if (c0.y & kCtlAllRows) {
+                if (g.nseg > 1) dflags = direct_lane_flags(g, tid, lane, stx, c2.y, c2.z, c2.z);
+                store_rows_direct_any<(MODE < 0 ? 0 : MODE)>((uint32_t)c2.w, rp, rowstride, px, valid && (dflags & kDirFull),
+                                                             (dflags & kDirFirst) != 0, (dflags & kDirLast) != 0);
+                if (valid && (dflags & kDirPartial)) {
                     // the frame's last tile column when W % 8 != 0 (dbde_util.cpp:281-289): its columns byte by byte
-                    const int ncol = (int)((dl.flags >> 8) & 15u);
+                    const int ncol = (int)((dflags >> 8) & 15u);
                     for (int c = 0; c < ncol; c++) {
                         const uint32_t sh = 8u * (uint32_t)(c & 3);
                         uint8_t *q = rp + c;
@@ -689,18 +619,6 @@ __global__ void __launch_bounds__(kDecThreads, MODE < 0 ? 3 : DBDE_DEC_DIRECT_MI
                         }
                     }
                 }
-#if !DBDE_DIR_ROWENDS
-                if ((dl.item & 1u) && (int)(dl.item >> 16) < c0.w) {
-                    const uint32_t e = (dl.item >> 1) & 1u, r = (dl.item >> 4) & 7u, slot = (dl.item >> 8) & 3u;
-                    const uint32_t rW = r * (uint32_t)g.W;
-                    const uint32_t a = ((uint32_t)c2.w + rW) & 7u;
-                    if (a) {
-                        const uint2 x = *reinterpret_cast<const uint2 *>(scr + 64 * slot + 8 * r);
-                        store_boundary_piece(part0 + dl.item_toff + rW, x, a, e);
-                    }
-                }
-                __syncwarp();                              // the scratch is read before the next partition overwrites it
-#endif
             } else {
                 // crop the padding (dbde_util.cpp:281-289): only rows < H and columns < W are written
                 const int rows_valid = valid ? min(8, g.H - 8 * (c2.x + sb)) : 0;
@@ -736,12 +654,6 @@ __global__ void __launch_bounds__(kDecThreads, MODE < 0 ? 3 : DBDE_DEC_DIRECT_MI
 // re-aligns row by row (2 x LDS.128 + 4 funnel shifts + one 16-byte global store per chunk): correct, but
 // 2x SLOWER (0.85 vs 0.43 ms per 1000 frames) -- ~90 instructions per image row on ONE warp that gets a
 // seventh of its scheduler; spread over the tile warps it would cost what the narrow stores cost now.
-#ifndef DBDE_STG_EDGE_OLD
-#define DBDE_STG_EDGE_OLD 0
-#endif
-#ifndef DBDE_STG_STATIC
-#define DBDE_STG_STATIC 1        // compile-time row shapes in the staged decoder (0: per-row alignment tests, for A/B runs)
-#endif
 constexpr int kStgStages = 2;                                    // input stages
 // One output image per CTA: 2 x 17 KiB in + 16.5 KiB out = 4 CTAs/SM.  Measured against two images (3 CTAs/SM):
 // +7-10 % on every 1001x1003 workload (mix 3.54 -> 3.81 TB/s) -- a fourth CTA hides more than a second image does.
@@ -758,11 +670,6 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
-// 8 bytes {lo, hi} to shared memory at any byte address, as naturally aligned pieces.  `a` = the
-// address's low bits, passed separately because the caller derives it from block-uniform values
-// (partition id -> frame, band -> global address of the row): the branches below are then uniform
-// branches, not divergent ones.  Three shapes: a % 4 == 0 -> 8 or 4+4; a % 4 == 2 -> 2+4+2;
-// odd -> 1+2+2+2+1 (the same code serves a % 4 == 1 and 3: every 2-byte piece lands on an even address).
 __device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
     asm volatile("{ .reg .b16 t; cvt.u16.u32 t, %1; st.shared.u16 [%0], t; }" ::"r"(addr), "r"(v) : "memory");
@@ -771,25 +678,6 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatil
 __device__ __forceinline__ void sts_v2u32(uint32_t addr, uint32_t lo, uint32_t hi) {
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(lo), "r"(hi) : "memory");
 }
-__device__ __forceinline__ void sts_row8(uint32_t addr, uint32_t a, uint32_t lo, uint32_t hi) {
-    if (a & 1u) {
-        sts_u8(addr, lo);
-        sts_u16(addr + 1, lo >> 8);
-        sts_u16(addr + 3, __funnelshift_r(lo, hi, 24));
-        sts_u16(addr + 5, hi >> 8);
-        sts_u8(addr + 7, hi >> 24);
-    } else if (a & 2u) {
-        sts_u16(addr, lo);
-        sts_u32(addr + 2, __funnelshift_r(lo, hi, 16));
-        sts_u16(addr + 6, hi >> 16);
-    } else if (a & 4u) {
-        sts_u32(addr, lo);
-        sts_u32(addr + 4, hi);
-    } else {
-        sts_v2u32(addr, lo, hi);
-    }
-}
-
 // The eight rows of a tile with every alignment known at compile time (WM = W & 7, A0 = alignment of row 0,
 // a switch case per partition): each row is its naturally aligned pieces at immediate offsets with constant
 // shifts -- 8 | 4+4 | 2+4+2 | 1+2+4+1 | 1+4+2+1 -- and no alignment test is executed per row.
@@ -937,31 +825,11 @@ __global__ void __launch_bounds__(kStgThreads, kStgOut == 1 ? 4 : 3) dbde_decode
             const int rows_valid = valid ? min(8, g.H - 8 * (y0 + sb)) : 0;
             uint32_t rp = img + toff;
             if (rows_valid == 8 && ncol == 8) {
-#if DBDE_STG_STATIC
                 sts_rows_static_any<WM>(ag, rp, (uint32_t)g.W, px);      // `ag & 7` is the same in every lane: a uniform switch
-#else
-                uint32_t a = ag;                            // image row alignment (tiles are 8 bytes apart: same for every lane)
-#pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    sts_row8(rp, a, px[2 * r], px[2 * r + 1]);
-                    rp += g.W;
-                    a += g.W;
-                }
-#endif
             } else {
                 // last tile column of an odd-width frame / last band of an odd-height one: only the
                 // valid columns and rows (dbde_util.cpp:281-289); a few lanes per partition.  Column by
                 // column, so the common one-or-two-column edge costs one or two passes over the rows.
-#if DBDE_STG_EDGE_OLD
-#pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    if (r < rows_valid) {
-                        const uint64_t x = ((uint64_t)px[2 * r + 1] << 32) | px[2 * r];
-                        for (int c = 0; c < ncol; c++) sts_u8(rp + c, (uint32_t)(x >> (8 * c)));
-                    }
-                    rp += g.W;
-                }
-#else
                 // (lanes past the partition's tiles come here too, with rows_valid == 0: they must not loop)
                 const int nc = rows_valid > 0 ? ncol : 0;
                 for (int c = 0; c < nc; c++) {
@@ -973,7 +841,6 @@ __global__ void __launch_bounds__(kStgThreads, kStgOut == 1 ? 4 : 3) dbde_decode
                         q += g.W;
                     }
                 }
-#endif
             }
             fence_proxy_async();                           // my generic-proxy writes, then the store warp's bulk read
             __syncwarp();
@@ -985,9 +852,8 @@ __global__ void __launch_bounds__(kStgThreads, kStgOut == 1 ? 4 : 3) dbde_decode
 
 size_t dec_smem_bytes(const PartGeom &g) {
     (void)g;
-    return ((sizeof(DecSmem) + 127) & ~(size_t)127) + (size_t)kDecStages * kDecStageBytes + kConsumerWarps * kDirScratchPerWarp;
+    return ((sizeof(DecSmem) + 127) & ~(size_t)127) + (size_t)kDecStages * kDecStageBytes;
 }
-static size_t dec_fast_smem_bytes() { return ((sizeof(DecSmem) + 127) & ~(size_t)127) + (size_t)kDecStages * kDecStageBytes; }
 
 cudaError_t launch_decode_scan(const DecParams &P, cudaStream_t stream) {
     if (P.nframes <= 0) return cudaSuccess;
@@ -1001,12 +867,9 @@ static size_t stg_smem_bytes() {
 
 template <typename Kern>
 static cudaError_t launch_persistent(Kern kern, const DecParams &P, int threads, size_t smem, int num_sms, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+    cudaError_t e = cached_occupancy((const void *)kern, threads, smem, &occ);
     if (e != cudaSuccess) return e;
-    if (occ < 1) return cudaErrorLaunchOutOfResources;
     unsigned grid = (unsigned)(num_sms * occ);
     if (grid > P.nparts) grid = P.nparts;
     if (grid == 0) return cudaSuccess;
@@ -1025,7 +888,7 @@ static bool odd_decode_staged() {
 
 cudaError_t launch_decode(const DecParams &P, bool fast, int num_sms, cudaStream_t stream) {
     const size_t smem = dec_smem_bytes(P.g);
-    if (fast) return launch_persistent(dbde_decode_kernel<-1>, P, kDecThreads, dec_fast_smem_bytes(), num_sms, stream);
+    if (fast) return launch_persistent(dbde_decode_kernel<-1>, P, kDecThreads, smem, num_sms, stream);
     if (P.g.nseg == 1 && odd_decode_staged()) {
         const size_t ss = stg_smem_bytes();
         switch (P.g.W & 7) {

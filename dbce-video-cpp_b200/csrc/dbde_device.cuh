@@ -273,48 +273,26 @@ __device__ __forceinline__ uint32_t squeeze4(uint32_t d, uint32_t c1, uint32_t c
     uint32_t p = d + odd * c1;
     return p + (p >> 16) * c2;
 }
-// inverse: one 4k-bit field -> 4 bytes, as two mask-and-multiply-add steps with no shifts:
-//   q = l + 2^2k*h  ->  p = l + 2^16*h = q + (q & hmask) * (2^(16-2k) - 1)       hmask = bits [2k, 4k)
-//   p = e + 2^k*o (per u16)  ->  w = e + 2^8*o = p + (p & omask) * (2^(8-k) - 1)   omask = bits [k, 2k) of both halves
-// The masked values are the moved fields still at their old places, so the multipliers are the
-// integers 2^(distance) - 1 and no product leaves 32 bits (h*c2s < 2^(16+2k), o*c1s < 2^(24+k)).
-// Four instructions per word (LOP3, IMAD, LOP3, IMAD); the first version shifted the fields down
-// before multiplying (SHF, IMAD, SHF, LOP3, IMAD).  q must be zero above bit 4k.
+// inverse: one 4k-bit field -> 4 bytes
+//   q = l + 2^2k*h -> p = q + h*(65536 - 2^2k);   p = e + 2^k*o (per u16) -> w = p + o*(256 - 2^k)
+// (SHF, IMAD, SHF, LOP3, IMAD.  A shift-free form -- p = q + (q & hmask)*(2^(16-2k) - 1), w = p + (p & omask)*(2^(8-k) - 1),
+// four instructions -- was measured and is SLOWER: micro-2048 decode 5.78 -> 5.67 TB/s, low-4096 5.05 -> 4.20.)
 struct SpreadK {
-    uint32_t hmask, c2s, omask, c1s;
+    uint32_t k, c2n, kmask2, c1n;
 };
 __device__ __forceinline__ SpreadK spread_consts(int k) {           // k = 1..8
     SpreadK s;
-    s.hmask = ((1u << (2 * k)) - 1u) << (2 * k);
-    s.c2s = (1u << (16 - 2 * k)) - 1u;
-    s.omask = (((1u << k) - 1u) << k) * 0x00010001u;
-    s.c1s = (1u << (8 - k)) - 1u;
+    s.k = (uint32_t)k;
+    s.c2n = 65536u - (1u << (2 * k));
+    s.kmask2 = ((1u << k) - 1u) * 0x00010001u;
+    s.c1n = 256u - (1u << k);
     return s;
 }
-#ifndef DBDE_SPREAD_OLD
-#define DBDE_SPREAD_OLD 1
-#endif
-#if DBDE_SPREAD_OLD
-__device__ __forceinline__ SpreadK spread_consts_old(int k) {
-    SpreadK s;
-    s.hmask = (uint32_t)k;
-    s.c2s = 65536u - (1u << (2 * k));
-    s.omask = ((1u << k) - 1u) * 0x00010001u;
-    s.c1s = 256u - (1u << k);
-    return s;
-}
-#define spread_consts spread_consts_old
 __device__ __forceinline__ uint32_t spread4(uint32_t q, const SpreadK &s) {
-    const uint32_t p = q + (q >> (2 * s.hmask)) * s.c2s;
-    const uint32_t odd = (p >> s.hmask) & s.omask;
-    return p + odd * s.c1s;
+    const uint32_t p = q + (q >> (2 * s.k)) * s.c2n;
+    const uint32_t odd = (p >> s.k) & s.kmask2;
+    return p + odd * s.c1n;
 }
-#else
-__device__ __forceinline__ uint32_t spread4(uint32_t q, const SpreadK &s) {
-    const uint32_t p = q + (q & s.hmask) * s.c2s;
-    return p + (p & s.omask) * s.c1s;
-}
-#endif
 
 // Concatenate sixteen 4K-bit fields LSB-first into K little-endian U64 words (2K u32 halves).
 // Everything is compile-time after unrolling.  Fields never overlap, so "or" is "add" and a

@@ -27,6 +27,9 @@
 #include "dbde_device.cuh"
 #include "dbde_kernels.h"
 
+#include <mutex>
+#include <vector>
+
 namespace dbde {
 
 // A warp with this many different non-zero depths packs with the depth-agnostic row packer.  Measured
@@ -559,6 +562,47 @@ cudaError_t launch_compact(const uint8_t *slots, uint64_t slot_stride, const uin
     return cudaGetLastError();
 }
 
+cudaError_t cached_occupancy(const void *kernel, int threads, size_t smem, int *occ) {
+    struct Entry {
+        const void *kernel;
+        int dev, threads, occ;
+        size_t smem;
+    };
+    struct Limit {                   // the kernel's dynamic shared-memory opt-in on a device: only ever raised
+        const void *kernel;
+        int dev;
+        size_t smem;
+    };
+    static std::mutex mu;
+    static std::vector<Entry> table;
+    static std::vector<Limit> limits;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    for (const Entry &x : table)
+        if (x.kernel == kernel && x.dev == dev && x.threads == threads && x.smem == smem) {
+            *occ = x.occ;
+            return cudaSuccess;
+        }
+    Limit *lim = nullptr;
+    for (Limit &l : limits)
+        if (l.kernel == kernel && l.dev == dev) lim = &l;
+    if (!lim || lim->smem < smem) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (lim) lim->smem = smem;
+        else limits.push_back(Limit{kernel, dev, smem});
+    }
+    int n = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem);
+    if (e != cudaSuccess) return e;
+    if (n < 1) return cudaErrorLaunchOutOfResources;
+    table.push_back(Entry{kernel, dev, threads, n, smem});
+    *occ = n;
+    return cudaSuccess;
+}
+
 size_t enc_smem_bytes(const PartGeom &g) {
     return ((sizeof(EncSmem) + 127) & ~(size_t)127) + (size_t)kEncStages * g.stage_bytes + 2 * (size_t)kConsumerWarps * kEncWarpBytes;
 }
@@ -583,12 +627,9 @@ cudaError_t launch_encode(const EncParams &Pin, bool fast, int num_sms, cudaStre
         case 6: kern = dbde_encode_kernel<false, false, true, 6>; break;
         default: kern = dbde_encode_kernel<false, false, true, 7>; break;
     }
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kEncThreads, smem);
+    cudaError_t e = cached_occupancy((const void *)kern, kEncThreads, smem, &occ);
     if (e != cudaSuccess) return e;
-    if (occ < 1) return cudaErrorLaunchOutOfResources;
     unsigned grid = (unsigned)(num_sms * occ);
     if (grid > P.nparts) grid = P.nparts;
     if (grid == 0) return cudaSuccess;

@@ -74,6 +74,11 @@ cudaError_t launch_encode16(const Enc16Params &P, int num_sms, cudaStream_t stre
 cudaError_t launch_decode16_scan(const Dec16Params &P, cudaStream_t stream);
 cudaError_t launch_decode16(const Dec16Params &P, int num_sms, cudaStream_t stream);
 
+// The persistent kernels' launch configuration (dynamic shared memory opt-in + resident CTAs per SM) is a
+// property of (device, kernel, shared-memory size): looked up once and remembered, because the two runtime
+// calls cost as much as the launch itself when a caller encodes one frame per call.
+cudaError_t cached_occupancy(const void *kernel, int threads, size_t smem, int *occ);
+
 size_t enc_smem_bytes(const PartGeom &g);
 size_t dec_smem_bytes(const PartGeom &g);
 cudaError_t launch_encode(const EncParams &P, bool fast, int num_sms, cudaStream_t stream);

@@ -7,11 +7,11 @@ g++ -O2 -std=c++14 -pthread -Iinclude scratch/dropin_mt.cpp -L$LIBDIR -ldbde_b20
 [ -f oracle/_ref/dbde_util.o ] && g++ -O2 -std=c++14 -pthread -Iinclude scratch/dropin_mt.cpp oracle/_ref/dbde_util.o -o scratch/dropin_mt_ref
 for mode in 0 1; do
   for T in 1 4 16; do
-    echo -n "b200: "; scratch/dropin_mt_b200 2048 2048 $((T > 4 ? 60 : 100)) $mode $T
-    [ -x scratch/dropin_mt_ref ] && { echo -n "ref : "; scratch/dropin_mt_ref 2048 2048 $((T > 4 ? 60 : 100)) $mode $T; }
+    echo -n "b200: "; timeout 90 scratch/dropin_mt_b200 2048 2048 $((T > 4 ? 60 : 100)) $mode $T
+    [ -x scratch/dropin_mt_ref ] && { echo -n "ref : "; timeout 90 scratch/dropin_mt_ref 2048 2048 $((T > 4 ? 60 : 100)) $mode $T; }
   done
 done
 for T in 1 16; do
-  echo -n "b200: "; scratch/dropin_mt_b200 1001 1003 200 0 $T
-  [ -x scratch/dropin_mt_ref ] && { echo -n "ref : "; scratch/dropin_mt_ref 1001 1003 200 0 $T; }
+  echo -n "b200: "; timeout 90 scratch/dropin_mt_b200 1001 1003 200 0 $T
+  [ -x scratch/dropin_mt_ref ] && { echo -n "ref : "; timeout 90 scratch/dropin_mt_ref 1001 1003 200 0 $T; }
 done
