@@ -275,8 +275,11 @@ __device__ __forceinline__ uint32_t squeeze4(uint32_t d, uint32_t c1, uint32_t c
 }
 // inverse: one 4k-bit field -> 4 bytes
 //   q = l + 2^2k*h -> p = q + h*(65536 - 2^2k);   p = e + 2^k*o (per u16) -> w = p + o*(256 - 2^k)
-// (SHF, IMAD, SHF, LOP3, IMAD.  A shift-free form -- p = q + (q & hmask)*(2^(16-2k) - 1), w = p + (p & omask)*(2^(8-k) - 1),
-// four instructions -- was measured and is SLOWER: micro-2048 decode 5.78 -> 5.67 TB/s, low-4096 5.05 -> 4.20.)
+// (SHF, IMAD, SHF, LOP3, IMAD: three ALU-pipe and two FMA-pipe instructions, which the scheduler pairs.  Measured
+// alternatives, both rejected: a shift-free form p = q + (q & hmask)*(2^(16-2k) - 1), w = p + (p & omask)*(2^(8-k) - 1) --
+// the compiler turns x*(2^n - 1) into shift-and-subtract, all on the ALU pipe: low-4096 decode 5.05 -> 4.20 TB/s; with the
+// multiplies forced (mad.lo) it is neutral, 4.79 vs 4.82 on mix-1001x1003 -- and the two shifts as multiply-high by a
+// power of two, which moves them to the FMA pipe but IMAD.HI issues slowly: 4.82 -> 4.35 TB/s.)
 struct SpreadK {
     uint32_t k, c2n, kmask2, c1n;
 };
