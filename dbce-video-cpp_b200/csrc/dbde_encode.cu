@@ -36,8 +36,13 @@ namespace dbde {
 // (mix-2048): never 4.11 TB/s, 4 -> 5.06, 3 -> 5.05; micro-2048 unchanged within noise.
 constexpr int kEncVarMinDepths = 4;
 
+// Copy-out with 16-byte stores (the north star's "128-bit vectorised stores") is implemented and measured, and
+// loses to 8-byte stores on everything but all-depth-8 noise (algorithmic TB/s, 8-byte vs 16-byte: micro-2048
+// 6.10 vs 6.06, low-4096 5.29 vs 5.18, mix-1001x1003 4.67 vs 4.65, noise-2048 6.24 vs 6.29): a warp's run starts
+// on an odd word half the time, so the vector path needs a leading and a trailing single-word store and two
+// 8-byte shared loads per vector, and the run is only ~100 words long.  -DDBDE_ENC_COPY16=1 builds it.
 #ifndef DBDE_ENC_COPY16
-#define DBDE_ENC_COPY16 1       // copy-out with 16-byte stores (0: 8-byte stores, for A/B runs)
+#define DBDE_ENC_COPY16 0
 #endif
 constexpr int kEncRing = 4;        // bookkeeping slots (aggregates, bases): a tile warp is <= 2 partitions ahead of the scan warp
 constexpr int kEncThreads = kTilesPerPart + 64;
@@ -337,10 +342,9 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
             if (((uintptr_t)dst & 7) == 0) {
                 // 16-byte stores: one leading word when the run starts on an odd word, then pairs of words
                 // (the warp's staging region is 16-byte aligned, so an even start also loads 16 bytes at a time)
-                const uint32_t head = ((uint32_t)(uintptr_t)dst >> 3) & 1u;
-                const uint32_t npair = (n - min(head, n)) >> 1;
+                const uint32_t head = n ? ((uint32_t)(uintptr_t)dst >> 3) & 1u : 0u;
+                const uint32_t npair = (n - head) >> 1;
                 if (head) {
-                    if (lane == 0 && n) st_stream_u64(dst, *reinterpret_cast<const uint64_t *>(src));
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         if (32u * j >= npair) break;
@@ -359,9 +363,13 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
                         if (i < npair) st_stream_v4u32(dst + 16 * i, *reinterpret_cast<const uint4 *>(src + 16 * i));
                     }
                 }
-                // the last word of a run with an odd number of words after the head
-                if (lane == 31 && n > head && ((n - head) & 1u))
-                    st_stream_u64(dst + 8 * (n - 1), *reinterpret_cast<const uint64_t *>(src + 8 * (n - 1)));
+                // the single words at the ends -- the leading one of a run that starts on an odd word (lane 0) and
+                // the last one of a run with an odd number of words after it (lane 31) -- in ONE predicated store
+                const bool tail = ((n - head) & 1u) != 0u;
+                if ((lane == 0 && head) || (lane == 31 && tail)) {
+                    const uint32_t w = lane == 0 ? 0u : n - 1u;
+                    st_stream_u64(dst + 8 * w, *reinterpret_cast<const uint64_t *>(src + 8 * w));
+                }
 #else
             if (((uintptr_t)dst & 7) == 0) {
 #pragma unroll
