@@ -385,12 +385,9 @@ static size_t smem16() { return (size_t)kWordBytesPadded16; }
 
 template <typename Kern, typename Params>
 static cudaError_t launch16(Kern kern, const Params &P, unsigned nparts, int num_sms, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16());
-    if (e != cudaSuccess) return e;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kT16, smem16());
+    cudaError_t e = cached_occupancy((const void *)kern, kT16, smem16(), &occ);
     if (e != cudaSuccess) return e;
-    if (occ < 1) return cudaErrorLaunchOutOfResources;
     unsigned grid = (unsigned)(num_sms * occ);
     if (grid > nparts) grid = nparts;
     if (grid == 0) return cudaSuccess;

@@ -154,14 +154,6 @@ static bool dims_ok(int W, int H, int nframes) {
     return wh <= 0x0FFFFFFF && (long long)W * H <= 0x7FFFFFFFLL;
 }
 
-// where a stream should start inside a 16-byte-aligned buffer so that the first frame's U64
-// words are 16-byte aligned (record sizes are multiples of 8 when wh % 4 == 0, so every
-// payload then stays 8-byte aligned)
-static size_t payload_align_delta(int W, int H) {
-    const size_t wh = (size_t)((W + 7) / 8) * ((H + 7) / 8);
-    return (16 - (32 + 2 * wh) % 16) % 16;
-}
-
 // ------------------------------------------------------------------ format variants
 // The reference's two compile-time variants.  Building this library with the same
 // macros makes them the defaults; dbde_b200_set_format_variants() switches them at run time.
@@ -612,10 +604,27 @@ static int relay_d2h(dbde_b200_ctx *c, HostSlot &s, uint8_t *dst, const uint8_t 
 }
 
 // ------------------------------------------------------------------ host-buffer hot path
-static int default_chunk(const dbde_b200_ctx *c, int W, int H, int nframes) {
+// What differs on the host path between the reference's 8-bit records and the DBDE16 extension: bytes per
+// frame, slot stride, where a slot's record starts so that its U64 words are 16-byte aligned.
+struct HostFmt {
+    bool u16;
+    size_t px, stride, delta;
+    size_t stream_bound(int n) const { return stride * (size_t)(n < 0 ? 0 : n) + 16; }
+};
+static HostFmt host_fmt(int W, int H, bool u16) {
+    HostFmt f;
+    const size_t wh = (size_t)((W + 7) / 8) * ((H + 7) / 8);
+    f.u16 = u16;
+    f.px = (size_t)W * H * (u16 ? 2 : 1);
+    f.stride = u16 ? dbde_b200_slot_stride16(W, H) : dbde_b200_slot_stride(W, H);
+    f.delta = (16 - (32 + (u16 ? 3 : 2) * wh) % 16) % 16;
+    return f;
+}
+
+static int default_chunk(const dbde_b200_ctx *c, int W, int H, int nframes, bool u16 = false) {
     int n = c->chunk_frames;
     if (n <= 0) {
-        const size_t px = (size_t)W * H;
+        const size_t px = (size_t)W * H * (u16 ? 2 : 1);
         n = (int)((64u << 20) / (px ? px : 1));
         if (n < 1) n = 1;
     }
@@ -680,11 +689,12 @@ struct EncSequencer {
 // Worker `my` of `nworkers`: encodes chunks my, my + nworkers, ... of the batch on context c.
 static int encode_host_worker(dbde_b200_ctx *c, const uint8_t *frames_host, int W, int H, uint64_t first_index,
                               int nframes, uint8_t *out_host, size_t out_capacity, uint64_t *frame_offsets_host,
-                              int chunk, int my, int nworkers, EncSequencer *seq) {
+                              int chunk, int my, int nworkers, EncSequencer *seq, bool u16 = false) {
     CK(cudaSetDevice(c->device));
-    const size_t px = (size_t)W * H;
-    const size_t delta = payload_align_delta(W, H);
-    const size_t need_a = px * chunk + 32, need_b = dbde_b200_stream_bound(W, H, chunk) + 32;
+    const HostFmt F = host_fmt(W, H, u16);
+    const size_t px = F.px;
+    const size_t delta = F.delta;
+    const size_t need_a = px * chunk + 32, need_b = F.stream_bound(chunk) + 32;
     const int nchunks = (nframes + chunk - 1) / chunk;
     const int mine = nchunks > my ? (nchunks - my + nworkers - 1) / nworkers : 0;
     const int ns = mine < c->nslots ? mine : c->nslots;            // a one-frame call sets up one slot
@@ -695,7 +705,7 @@ static int encode_host_worker(dbde_b200_ctx *c, const uint8_t *frames_host, int 
         if (!rc) rc = ensure_bounce(c, c->slots[i], in_pageable ? px * chunk : 0, out_pageable ? need_b : 0);
         if (rc) return rc;
     }
-    const size_t stride = dbde_b200_slot_stride(W, H);
+    const size_t stride = F.stride;
     // finish(): wait for a chunk's kernels, learn the record sizes, claim the chunk's place in the
     // stream, and queue ONE D2H copy of its records -- already laid back to back on the device
     // (a one-frame chunk's record is contiguous in its slot as it is: no compaction pass).
@@ -747,8 +757,10 @@ static int encode_host_worker(dbde_b200_ctx *c, const uint8_t *frames_host, int 
             CK(cudaMemcpyAsync(s.d_a, frames_host + px * s.first, px * s.n, cudaMemcpyHostToDevice, s.st));
         }
         prof.mark(1, "h2d");
-        rc_all = dbde_b200_encode_device(c, s.d_a, W, H, first_index + s.first, s.n, s.d_b + delta, need_b - 32, stride,
-                                         s.d_off, s.d_size, s.st);
+        rc_all = u16 ? dbde_b200_encode16_device(c, (const uint16_t *)s.d_a, W, H, first_index + s.first, s.n, s.d_b + delta,
+                                                 need_b - 32, stride, s.d_off, s.d_size, s.st)
+                     : dbde_b200_encode_device(c, s.d_a, W, H, first_index + s.first, s.n, s.d_b + delta, need_b - 32, stride,
+                                               s.d_off, s.d_size, s.st);
         if (rc_all) break;
         CK(cudaMemcpyAsync(s.h_size, s.d_size, 8 * (size_t)s.n, cudaMemcpyDeviceToHost, s.st));
         if (chunk > 1) {
@@ -791,7 +803,7 @@ extern "C" int dbde_b200_encode_host(dbde_b200_ctx *c, const uint8_t *frames_hos
 
 static int decode_host_impl(dbde_b200_ctx *c, const uint8_t *stream_host, size_t stream_bytes,
                             const uint64_t *frame_offsets_host, int W, int H, int nframes, uint8_t *frames_host,
-                            uint32_t *status_host, uint64_t *indices_host, bool scan_only) {
+                            uint32_t *status_host, uint64_t *indices_host, bool scan_only, bool u16 = false) {
     if (!c || !dims_ok(W, H, nframes) ||
         (nframes > 0 && (!stream_host || !frame_offsets_host || (!frames_host && !scan_only) || !status_host)))
         return fail(DBDE_B200_E_INVALID, "decode_host: bad argument");
@@ -802,9 +814,10 @@ static int decode_host_impl(dbde_b200_ctx *c, const uint8_t *stream_host, size_t
         if (frame_offsets_host[i] > end || end > stream_bytes)
             return fail(DBDE_B200_E_INVALID, "decode_host: frame offsets must ascend within the stream");
     }
-    const size_t px = (size_t)W * H;
-    const int chunk = default_chunk(c, W, H, nframes);
-    const size_t delta = payload_align_delta(W, H);
+    const HostFmt F = host_fmt(W, H, u16);
+    const size_t px = F.px;
+    const int chunk = default_chunk(c, W, H, nframes, u16);
+    const size_t delta = F.delta;
     const int nchunks = (nframes + chunk - 1) / chunk;
     size_t need_a = 0;
     for (int ci = 0; ci < nchunks; ci++) {
@@ -817,7 +830,7 @@ static int decode_host_impl(dbde_b200_ctx *c, const uint8_t *stream_host, size_t
     // Size the stream staging for the worst case of this geometry, not for this call's records: a caller
     // that decodes frame after frame (the drop-in dbde_unpack_frame, the file walker) would otherwise
     // pay a cudaFree + cudaMalloc every time a record is larger than any before it.
-    const size_t bound_a = dbde_b200_stream_bound(W, H, chunk) + 64;
+    const size_t bound_a = F.stream_bound(chunk) + 64;
     if (need_a < bound_a) need_a = bound_a;
     const size_t need_b = scan_only ? 0 : px * chunk + 32;
     const int ns = nchunks < c->nslots ? nchunks : c->nslots;
@@ -882,8 +895,10 @@ static int decode_host_impl(dbde_b200_ctx *c, const uint8_t *stream_host, size_t
             CK(cudaMemcpyAsync(s.d_a + delta, stream_host + b0, b1 - b0, cudaMemcpyHostToDevice, s.st));
         }
         prof.mark(1, "h2d");
-        rc_all = decode_device_impl(c, s.d_a + delta, b1 - b0, s.d_off, W, H, s.n, s.d_b, s.d_status, s.d_index, s.st,
-                                    scan_only);
+        rc_all = u16 ? dbde_b200_decode16_device(c, s.d_a + delta, b1 - b0, s.d_off, W, H, s.n, (uint16_t *)s.d_b, s.d_status,
+                                                 s.d_index, s.st)
+                     : decode_device_impl(c, s.d_a + delta, b1 - b0, s.d_off, W, H, s.n, s.d_b, s.d_status, s.d_index, s.st,
+                                          scan_only);
         if (rc_all) break;
         CK(cudaMemcpyAsync(s.h_status, s.d_status, 4 * (size_t)s.n, cudaMemcpyDeviceToHost, s.st));
         if (indices_host) CK(cudaMemcpyAsync(s.h_index, s.d_index, 8 * (size_t)s.n, cudaMemcpyDeviceToHost, s.st));
@@ -992,44 +1007,21 @@ extern "C" int dbde_b200_decode16_device(dbde_b200_ctx *c, const uint8_t *stream
     return 0;
 }
 
-// Host-buffer forms: one staged batch at a time (H2D, kernels, record compaction, D2H), synchronous.
-// The 8-bit path's chunk pipeline is not replicated for the extension.
+// Host-buffer forms: the 8-bit path's chunk pipeline (staging slots in flight, records compacted on the
+// device, pageable buffers relayed through the copy pool), with the DBDE16 kernels underneath.
 extern "C" int dbde_b200_encode16_host(dbde_b200_ctx *c, const uint16_t *frames_host, int W, int H, uint64_t first_index,
                                        int nframes, uint8_t *out_host, size_t out_capacity, uint64_t *frame_offsets_host) {
     if (!c || !dims_ok(W, H, nframes) || (nframes > 0 && (!frames_host || !out_host || !frame_offsets_host)))
         return fail(DBDE_B200_E_INVALID, "encode16_host: bad argument");
-    if (frame_offsets_host) frame_offsets_host[0] = 0;
-    if (nframes == 0) return 0;
-    CK(cudaSetDevice(c->device));
-    const size_t px2 = 2 * (size_t)W * H, stride = dbde_b200_slot_stride16(W, H);
-    int chunk = (int)((128u << 20) / (px2 ? px2 : 1));
-    if (chunk < 1) chunk = 1;
-    if (chunk > nframes) chunk = nframes;
-    HostSlot &s = c->slots[0];
-    int rc = ensure_slot(c, s, px2 * chunk + 32, stride * chunk + 64, stride * chunk + 64, chunk);
-    if (rc) return rc;
-    size_t pos = 0;
-    for (int first = 0; first < nframes; first += chunk) {
-        const int n = nframes - first < chunk ? nframes - first : chunk;
-        CK(cudaMemcpyAsync(s.d_a, frames_host + (size_t)first * W * H, px2 * n, cudaMemcpyHostToDevice, s.st));
-        rc = dbde_b200_encode16_device(c, (const uint16_t *)s.d_a, W, H, first_index + first, n, s.d_b, stride * n, stride, s.d_off,
-                                       s.d_size, s.st);
-        if (rc) return rc;
-        CK(cudaMemcpyAsync(s.h_size, s.d_size, 8 * (size_t)n, cudaMemcpyDeviceToHost, s.st));
-        CK(launch_compact(s.d_b, stride, s.d_size, n, s.d_c, s.st));
-        c->launches += 1;
-        CK(cudaStreamSynchronize(s.st));
-        uint64_t total = 0;
-        for (int i = 0; i < n; i++) {
-            frame_offsets_host[first + i] = pos + total;
-            total += s.h_size[i];
-        }
-        if (pos + total > out_capacity) return fail(DBDE_B200_E_CAPACITY, "encode16_host: out_capacity too small");
-        CK(cudaMemcpyAsync(out_host + pos, s.d_c, total, cudaMemcpyDeviceToHost, s.st));
-        CK(cudaStreamSynchronize(s.st));
-        pos += total;
+    if (nframes == 0) {
+        if (frame_offsets_host) frame_offsets_host[0] = 0;
+        return 0;
     }
-    frame_offsets_host[nframes] = pos;
+    EncSequencer seq;
+    int rc = encode_host_worker(c, (const uint8_t *)frames_host, W, H, first_index, nframes, out_host, out_capacity,
+                                frame_offsets_host, default_chunk(c, W, H, nframes, true), 0, 1, &seq, true);
+    if (rc) return rc;
+    frame_offsets_host[nframes] = seq.out_pos;
     return 0;
 }
 
@@ -1038,52 +1030,8 @@ extern "C" int dbde_b200_decode16_host(dbde_b200_ctx *c, const uint8_t *stream_h
                                        uint32_t *status_host, uint64_t *indices_host) {
     if (!c || !dims_ok(W, H, nframes) || (nframes > 0 && (!stream_host || !frame_offsets_host || !frames_host || !status_host)))
         return fail(DBDE_B200_E_INVALID, "decode16_host: bad argument");
-    if (nframes == 0) return 0;
-    CK(cudaSetDevice(c->device));
-    for (int i = 0; i < nframes; i++) {
-        const uint64_t end = i + 1 < nframes ? frame_offsets_host[i + 1] : stream_bytes;
-        if (frame_offsets_host[i] > end || end > stream_bytes)
-            return fail(DBDE_B200_E_INVALID, "decode16_host: frame offsets must ascend within the stream");
-    }
-    const size_t px2 = 2 * (size_t)W * H;
-    int chunk = (int)((128u << 20) / (px2 ? px2 : 1));
-    if (chunk < 1) chunk = 1;
-    if (chunk > nframes) chunk = nframes;
-    size_t need_a = 0;
-    for (int first = 0; first < nframes; first += chunk) {
-        const int n = nframes - first < chunk ? nframes - first : chunk;
-        const uint64_t b0 = frame_offsets_host[first], b1 = first + n < nframes ? frame_offsets_host[first + n] : stream_bytes;
-        if (b1 - b0 > need_a) need_a = b1 - b0;
-    }
-    const size_t bound_a = dbde_b200_slot_stride16(W, H) * chunk;
-    if (need_a < bound_a) need_a = bound_a;
-    HostSlot &s = c->slots[0];
-    int rc = ensure_slot(c, s, need_a + 64, px2 * chunk + 32, 0, chunk);
-    if (rc) return rc;
-    for (int first = 0; first < nframes; first += chunk) {
-        const int n = nframes - first < chunk ? nframes - first : chunk;
-        const uint64_t b0 = frame_offsets_host[first], b1 = first + n < nframes ? frame_offsets_host[first + n] : stream_bytes;
-        for (int i = 0; i < n; i++) s.h_off[i] = frame_offsets_host[first + i] - b0;
-        CK(cudaMemcpyAsync(s.d_off, s.h_off, 8 * (size_t)n, cudaMemcpyHostToDevice, s.st));
-        CK(cudaMemcpyAsync(s.d_a, stream_host + b0, b1 - b0, cudaMemcpyHostToDevice, s.st));
-        rc = dbde_b200_decode16_device(c, s.d_a, b1 - b0, s.d_off, W, H, n, (uint16_t *)s.d_b, s.d_status, s.d_index, s.st);
-        if (rc) return rc;
-        CK(cudaMemcpyAsync(status_host + first, s.d_status, 4 * (size_t)n, cudaMemcpyDeviceToHost, s.st));
-        if (indices_host) CK(cudaMemcpyAsync(indices_host + first, s.d_index, 8 * (size_t)n, cudaMemcpyDeviceToHost, s.st));
-        CK(cudaStreamSynchronize(s.st));
-        int run0 = 0;                                     // rejected frames keep the caller's pixels
-        for (int i = 0; i <= n; i++) {
-            const bool ok = i < n && status_host[first + i] == 0;
-            if (!ok) {
-                if (i > run0)
-                    CK(cudaMemcpyAsync(frames_host + (size_t)(first + run0) * W * H, s.d_b + px2 * run0, px2 * (size_t)(i - run0),
-                                       cudaMemcpyDeviceToHost, s.st));
-                run0 = i + 1;
-            }
-        }
-        CK(cudaStreamSynchronize(s.st));
-    }
-    return 0;
+    return decode_host_impl(c, stream_host, stream_bytes, frame_offsets_host, W, H, nframes, (uint8_t *)frames_host, status_host,
+                            indices_host, false, true);
 }
 
 // ------------------------------------------------------------------ multi-GPU sharding

@@ -164,7 +164,8 @@ DBDE_B200_API int dbde_b200_validate_host(dbde_b200_ctx *ctx, const uint8_t *str
  * (a reader tells the layouts apart by the minimum plane's length).  A frame whose pixels fit in 8 bits
  * gets exactly the 8-bit codec's depth plane and words.  Same conventions as the 8-bit entry points;
  * frames are W*H U16 per frame, tightly packed; fastest when W % 8 == 0 and the frame buffer is 16-byte
- * aligned.  The host forms stage one batch at a time (no chunk pipeline). */
+ * aligned.  The host forms share the 8-bit entry points' chunk pipeline (staging slots in flight, pageable
+ * buffers relayed through pinned bounce buffers). */
 DBDE_B200_API size_t dbde_b200_frame_record_bound16(int W, int H);    /* 32 + 131*wh */
 DBDE_B200_API size_t dbde_b200_slot_stride16(int W, int H);
 DBDE_B200_API int dbde_b200_encode16_device(dbde_b200_ctx *ctx, const uint16_t *frames_dev, int W, int H,
