@@ -125,6 +125,7 @@ static PartGeom make_geom(int W, int H, bool fast) {
     PartGeom g;
     g.W = W; g.H = H;
     g.w = (W + 7) / 8; g.h = (H + 7) / 8; g.wh = g.w * g.h;
+    g.linear = 0;
     int ntx_max;
     if (g.w > kTilesPerPart) {
         g.nseg = (g.w + kTilesPerPart - 1) / kTilesPerPart;
@@ -142,6 +143,21 @@ static PartGeom make_geom(int W, int H, bool fast) {
     g.pitch = pitch_of(ntx_max);
     while (g.G > 1 && 8 * g.G * g.pitch > 20480) g.G--;
     if (g.nseg == 1) g.ppf = (g.h + g.G - 1) / g.G;
+    // Band-aligned partitions leave lanes idle when the width does not fill them: 2304 pixels = 288 tiles is a
+    // 256-tile and a 32-tile segment per band (56 % of the lanes work), 1280 pixels = 160 tiles is one band per
+    // partition (63 %).  Aligned frames at least 32 tiles wide then use LINEAR partitions: 256 consecutive tiles
+    // of the row-major tile order, staged as the <= 256/w + 2 band pieces they consist of, side by side at the
+    // constant row pitch 2048 -- every lane has a tile (measured: 2304x2304 3.55 -> see DESIGN.md section 6).
+    if (fast && g.w >= 32 && g.w % kTilesPerPart != 0) {
+        const double used = g.nseg > 1 ? (double)g.w / (g.nseg * kTilesPerPart) : (double)(g.G * g.w) / kTilesPerPart;
+        if (used < 0.9 && getenv("DBDE_B200_NO_LINEAR") == nullptr) {
+            g.linear = 1;
+            g.nseg = 1;
+            g.G = 1;
+            g.ppf = (g.wh + kTilesPerPart - 1) / kTilesPerPart;
+            g.pitch = 8 * kTilesPerPart;
+        }
+    }
     int need = 8 * g.G * g.pitch;
     if (need < 64 * kTilesPerPart) need = 64 * kTilesPerPart;
     g.stage_bytes = ((need + 64 + 127) / 128) * 128;

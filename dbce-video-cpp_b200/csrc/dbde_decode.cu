@@ -533,11 +533,14 @@ __device__ __forceinline__ void dec_producer(const DecParams &P, DecSmemT<NSTAGE
 }
 
 // MODE -1: aligned frames (W % 16 == 0, H % 8 == 0, 16-byte aligned base): rows are stored as they are.
+// MODE -2: the same with linear partitions (make_geom): a lane finds its tile's band and column per partition.
 // MODE 0..7 = W & 7: every other geometry; rows are re-aligned across lanes (store_rows_direct) unless the
 //           partition has cropped rows (the frame's last band when H % 8 != 0), which are stored piecewise.
 template <int MODE>
-__global__ void __launch_bounds__(kDecThreads, MODE < 0 ? 3 : 4) dbde_decode_kernel(const DecParams P) {
+__global__ void __launch_bounds__(kDecThreads, MODE == -1 ? 3 : 4) dbde_decode_kernel(const DecParams P) {
     constexpr bool FAST = MODE < 0;
+    constexpr bool LIN = MODE == -2;          // aligned frame, linear partitions (a separate instantiation: its
+                                              // per-lane tile arithmetic must not cost the plain aligned kernel registers)
     extern __shared__ __align__(128) uint8_t smem_raw[];
     DecSmem &S = *reinterpret_cast<DecSmem *>(smem_raw);
     uint8_t *stages = smem_raw + ((sizeof(DecSmem) + 127) & ~127);
@@ -565,6 +568,9 @@ __global__ void __launch_bounds__(kDecThreads, MODE < 0 ? 3 : 4) dbde_decode_ker
         }
         const uint32_t toff = (uint32_t)(8 * sb) * (uint32_t)g.W + 8u * (uint32_t)stx;   // my tile inside a partition's pixels
         const size_t rowstride = (size_t)g.W;
+        // linear partitions (aligned frames only): my tile is tile tid after the partition's first one, i.e.
+        // lin_dy bands down and lin_dx columns right of it, wrapping once more if that passes the last column
+        const int lin_dy = LIN ? tid / g.w : 0, lin_dx = LIN ? tid - lin_dy * g.w : 0;
         // direct re-aligned stores: a lane's place in its image row is fixed for full-width partitions and is
         // worked out per partition for band segments of wider frames (the last segment is shorter)
         uint32_t dflags = 0;
@@ -593,6 +599,15 @@ __global__ void __launch_bounds__(kDecThreads, MODE < 0 ? 3 : 4) dbde_decode_ker
 
             uint8_t *const part0 = P.frames + (size_t)c0.z * fbytes + c1.w;       // the partition's first pixel
             uint8_t *rp = part0 + toff;
+            if (LIN) {
+                const int2 c2l = *reinterpret_cast<const int2 *>(&S.ctl[s].y0);   // first tile's band and column
+                int ty = c2l.x + lin_dy, tx = c2l.y + lin_dx;
+                if (tx >= g.w) {
+                    tx -= g.w;
+                    ty++;
+                }
+                rp = P.frames + (size_t)c0.z * fbytes + ((size_t)(8 * ty) * g.W + 8 * (size_t)tx);
+            }
             if (FAST) {
                 // no edges, 8-byte aligned rows: lane t stores 8 bytes of each row, a warp 256 contiguous bytes
                 if (valid) {
@@ -888,6 +903,7 @@ static bool odd_decode_staged() {
 
 cudaError_t launch_decode(const DecParams &P, bool fast, int num_sms, cudaStream_t stream) {
     const size_t smem = dec_smem_bytes(P.g);
+    if (fast && P.g.linear) return launch_persistent(dbde_decode_kernel<-2>, P, kDecThreads, smem, num_sms, stream);
     if (fast) return launch_persistent(dbde_decode_kernel<-1>, P, kDecThreads, smem, num_sms, stream);
     if (P.g.nseg == 1 && odd_decode_staged()) {
         const size_t ss = stg_smem_bytes();

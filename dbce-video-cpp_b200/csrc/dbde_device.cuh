@@ -23,6 +23,7 @@ constexpr int kMaxRowsPerPart = 8 * kMaxBandsPerPart;   // ... i.e. <= 64 pixel 
 // How a frame is cut into partitions (the unit of the scan and of one pipeline stage).
 //   w <= 256 tiles : a partition is G consecutive 8-row bands (G*w <= 256 tiles)
 //   w  > 256 tiles : a band is cut into nseg segments of <= 256 tiles
+//   linear         : tiles [256 q, 256 q + 256) of the row-major tile order, across band boundaries
 // Either way a partition's tiles are CONTIGUOUS in the frame's row-major tile order, so the
 // partition order is the order of the reference's running output pointer (dbde_util.cpp:155).
 struct PartGeom {
@@ -32,6 +33,8 @@ struct PartGeom {
     int ppf;      // partitions per frame
     int pitch;    // smem row pitch in bytes (multiple of 16)
     int stage_bytes;
+    int linear;   // 1: a partition is 256 CONSECUTIVE tiles of the frame's row-major tile order, whatever bands
+                  //    they fall in (aligned frames whose width would leave lanes idle otherwise, see make_geom)
 };
 
 struct PartInfo {
@@ -49,6 +52,15 @@ __host__ __device__ inline PartInfo part_info(const PartGeom &g, unsigned p) {
     PartInfo o;
     o.f = (int)(p / (unsigned)g.ppf);
     o.q = (int)(p - (unsigned)o.f * (unsigned)g.ppf);
+    if (g.linear) {
+        o.tfirst = o.q * kTilesPerPart;
+        o.nt = g.wh - o.tfirst < kTilesPerPart ? g.wh - o.tfirst : kTilesPerPart;
+        o.y0 = o.tfirst / g.w;
+        o.tx0 = o.tfirst - o.y0 * g.w;
+        o.nbands = (o.tx0 + o.nt + g.w - 1) / g.w;        // bands the partition touches
+        o.ntx = g.w;
+        return o;
+    }
     if (g.nseg > 1) {
         o.y0 = o.q / g.nseg;
         int seg = o.q - o.y0 * g.nseg;

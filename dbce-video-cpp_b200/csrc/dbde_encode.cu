@@ -144,7 +144,9 @@ __device__ __forceinline__ void load_rows_contig_any(uint32_t addr, uint32_t W, 
 }
 
 // WM: W & 7 for the CONTIG kernel (compile-time row shapes), 0 otherwise.
-template <bool FAST, bool WIDE, bool CONTIG, int WM = 0>
+// LIN: FAST with linear partitions (make_geom): staged like WIDE -- tile t at byte 8t of every row, pitch 2048 --
+//      but the frame's last partition may be short.
+template <bool FAST, bool WIDE, bool CONTIG, int WM = 0, bool LIN = false>
 __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     EncSmem &S = *reinterpret_cast<EncSmem *>(smem_raw);
@@ -215,6 +217,31 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
                     *reinterpret_cast<int4 *>(&S.ctl[s].q) = make_int4(pi.q, pi.y0, pi.tx0, (int)((uintptr_t)g0 - a0));
                     mbar_arrive_expect_tx(&S.full[s], (uint32_t)(a1 - a0));
                     tma_load_1d(stage, (const void *)a0, (uint32_t)(a1 - a0), &S.full[s]);
+                }
+                continue;
+            }
+            if (LIN) {
+                // linear partition: tiles [tfirst, tfirst + nt) of the row-major tile order = the tail of one band,
+                // whole bands, the head of another.  Each piece is 8 row copies of 8*ntx bytes, and the pieces sit
+                // side by side in the stage's 8 rows (pitch 2048), so tile t of the partition is at byte 8t of every
+                // row whatever band it came from.  Lane group i & 3 issues piece i (lane & 7 = the row).
+                if (lane == 0) {
+                    *reinterpret_cast<int4 *>(&S.ctl[s].part) = make_int4((int)p, pi.f, pi.tfirst, pi.nt);
+                    *reinterpret_cast<int4 *>(&S.ctl[s].q) = make_int4(pi.q, pi.y0, pi.tx0, 0);
+                    mbar_arrive_expect_tx(&S.full[s], 64u * (uint32_t)pi.nt);
+                }
+                __syncwarp();
+                int band = pi.y0, tx = pi.tx0, done = 0;
+                for (int i = 0; done < pi.nt; i++) {
+                    const int ntx = min(g.w - tx, pi.nt - done);
+                    if ((lane >> 3) == (i & 3)) {
+                        const int r = lane & 7;
+                        tma_load_1d(stage + (size_t)r * g.pitch + 8 * done, fptr + (size_t)(8 * band + r) * g.W + 8 * tx,
+                                    8u * (uint32_t)ntx, &S.full[s]);
+                    }
+                    done += ntx;
+                    tx = 0;
+                    band++;
                 }
                 continue;
             }
@@ -395,7 +422,7 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
 
             // ---- stage (1)->registers: 8 rows x 8 bytes
             uint32_t px[16];
-            if (WIDE) {
+            if (WIDE || LIN) {
                 const uint8_t *base = stage + 8 * tid;
 #pragma unroll
                 for (int r = 0; r < 8; r++) {
@@ -623,6 +650,7 @@ cudaError_t launch_encode(const EncParams &Pin, bool fast, int num_sms, cudaStre
     if (contig) P.g.pitch = P.g.W;        // the stage holds the partition's pixels exactly as they lie in the frame
     void (*kern)(const EncParams) = nullptr;
     if (wide) kern = dbde_encode_kernel<true, true, false>;
+    else if (fast && P.g.linear) kern = dbde_encode_kernel<true, false, false, 0, true>;
     else if (fast) kern = dbde_encode_kernel<true, false, false>;
     else if (!contig) kern = dbde_encode_kernel<false, false, false>;
     else switch (P.g.W & 7) {

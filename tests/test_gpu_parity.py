@@ -125,7 +125,11 @@ def test_golden_synthetic_streams(codec, golden):
 # ------------------------------------------------------------------ differential vs the oracle
 @pytest.mark.parametrize("W,H", [(8, 8), (16, 8), (1, 1), (3, 5), (7, 9), (9, 7), (17, 23), (64, 64), (100, 37),
                                  (257, 129), (255, 8), (256, 16), (264, 24), (1001, 83), (2048, 16), (2056, 24),
-                                 (2049, 9), (4096, 8), (4104, 16), (520, 520)])
+                                 (2049, 9), (4096, 8), (4104, 16), (520, 520),
+                                 # aligned widths that do not fill 256-tile partitions band by band: linear partitions
+                                 # (256 consecutive tiles across band boundaries), full and partial last partitions
+                                 (1280, 64), (2304, 48), (2560, 40), (1392, 104), (1104, 24), (4112, 16), (1280, 8),
+                                 (2304, 2304), (1280, 1024)])
 def test_sizes_and_edges(codec, W, H):
     rng = np.random.default_rng(W * 10007 + H)
     frames = np.stack([rand_frame(rng, W, H, ["classes", "noise", "flat"][i % 3]) for i in range(3)])
@@ -796,7 +800,8 @@ def test_file_writer_and_reader_roundtrip_against_the_oracle_file(codec, dropin)
 
 
 @pytest.mark.parametrize("kind,N,W,H", [("micro", 256, 2048, 2048), ("mix", 160, 1001, 1003), ("low", 40, 4096, 4096),
-                                        ("noise", 12, 2536, 2048), ("micro", 24, 4096, 4096)])
+                                        ("noise", 12, 2536, 2048), ("micro", 24, 4096, 4096), ("micro", 48, 2560, 2160),
+                                        ("mix", 96, 1280, 1024)])
 def test_baseline_configs_device_resident_at_scale(codec, kind, N, W, H):
     """BASELINE configs 2-4 (+ the reference's own 2536x2048 noise frame, + micro at 4096^2) as the bench
     runs them -- generated, encoded and decoded in HBM, hundreds of frames per launch so the persistent
@@ -851,7 +856,7 @@ def test_baseline_configs_device_resident_at_scale(codec, kind, N, W, H):
 
 
 @pytest.mark.parametrize("W,H,N", [(1001, 1003, 3), (13, 9, 5), (7, 5, 4), (2048, 16, 2), (264, 24, 3), (4100, 12, 2), (1004, 40, 3),
-                                   (1006, 24, 2), (259, 16, 3)])
+                                   (1006, 24, 2), (259, 16, 3), (2304, 24, 2), (1280, 40, 3)])
 def test_decoder_and_encoder_never_write_outside_their_buffers(codec, odd_decode, W, H, N):
     """guard bytes around the decoder's pixel output and the encoder's slots, at every misalignment of
     the output base: the generic store path assembles aligned 8-byte words across lanes, so a frame's
