@@ -139,7 +139,9 @@ static PartGeom make_geom(int W, int H, bool fast) {
         if (g.G > g.h) g.G = g.h;
         ntx_max = g.w;
     }
-    auto pitch_of = [&](int ntx) { return fast ? 8 * ntx : ((8 * ntx + 15) / 16) * 16 + 32; };
+    // odd sizes: a row's 16-byte hull is up to 30 bytes longer than the row, and for band segments (w > 256) the
+    // pitch is W modulo 16, which lets every row sit at its global alignment at a constant stride (dbde_encode.cu)
+    auto pitch_of = [&](int ntx) { return fast ? 8 * ntx : ((8 * ntx + 15) / 16) * 16 + 48 + (g.w > kTilesPerPart ? (W & 15) : 0); };
     g.pitch = pitch_of(ntx_max);
     while (g.G > 1 && 8 * g.G * g.pitch > 20480) g.G--;
     if (g.nseg == 1) g.ppf = (g.h + g.G - 1) / g.G;

@@ -403,7 +403,8 @@ __device__ __forceinline__ void store_rows_direct_any(uint32_t a0, uint8_t *rp, 
 // Reads the tile's depth and minimum from the staged planes and its k words from the staged payload,
 // returns the 64 pixels (+min applied) in px.  Warp-wide call (scan + vote).
 // Measured (mix-2048, all nine depths per warp): threshold 99 (never) 4.41 TB/s, 3 -> 5.71, 2 -> 5.70; micro-2048
-// is indifferent (5.80-5.92 in all three), low-4096 loses 7 % at 2.
+// is indifferent (5.80-5.92 in all three), low-4096 loses 7 % at 2.  Re-measured with the sliding-window unpacker:
+// threshold 2 costs low-4096 10 % and low-1001x1003 8 %, threshold 1 (always) the same and gains 2 % on noise only.
 constexpr int kDecVarMinDepths = 3;
 __device__ __forceinline__ void dec_unpack_tile(const uint8_t *stage, const uint4 &c1, uint32_t wbase, int tid, int lane,
                                                 bool valid, bool invert, uint32_t (&px)[16]) {
@@ -421,7 +422,9 @@ __device__ __forceinline__ void dec_unpack_tile(const uint8_t *stage, const uint
     // specialisation; from kDecVarMinDepths on, the depth-agnostic row unpacker is shorter.
     const uint32_t kinds = __reduce_or_sync(0xffffffffu, (1u << k) >> 1);
     const uint8_t *pay = stage + pres + 8 * (size_t)woff;
-    if (__popc(kinds) >= kDecVarMinDepths) {
+    // (a warp of nothing but depth-8 tiles also goes this way: the K = 8 specialisation reads its 64-byte payloads with
+    // 8-way bank conflicts, the sliding window does not -- noise-2048 5.71 -> 5.83 TB/s)
+    if (__popc(kinds) >= kDecVarMinDepths || kinds == 0x80u) {
         if (k > 0) {
             if (DBDE_DEC_VAR64 && (pres & 7u) == 0) unpack_rows_var64(pay, k, px, m4);
             else unpack_rows_var(pay, k, px, m4);

@@ -54,7 +54,6 @@ struct alignas(16) EncCtl {     // per-stage control block, written by the produ
     int nt;                     // tiles in this partition
     int q;                      // partition within the frame
     int y0, tx0, pad;           // first band / first tile column (generic path only)
-    uint16_t rowoff[kMaxRowsPerPart];   // byte offset of each row's first pixel inside its smem row
 };
 struct alignas(16) EncBase {    // per-stage, written by the scan warp
     uint8_t *frame;             // where this frame's record starts
@@ -96,9 +95,10 @@ constexpr int kWidePitch = 8 * kTilesPerPart;
 // WIDE : FAST and w % 256 == 0 (2048-, 4096-pixel-wide frames): every partition is one full 256-tile
 //        band segment, so the smem pitch is the constant 2048 (immediate-offset row loads) and no
 //        lane is ever idle.
-// CONTIG: odd sizes whose partitions span the full width (W <= 2048): the partition's pixels are one
-//        contiguous byte range of the frame, staged with ONE bulk copy of its 16-byte hull at row
-//        pitch W; a lane's row is then `first row + r * W`, read as aligned words + funnel shift.
+// CONTIG: every odd size.  Full-width partitions (W <= 2048): the partition's pixels are one contiguous byte
+//        range of the frame, staged with ONE bulk copy of its 16-byte hull at row pitch W.  Band segments of
+//        wider frames: eight per-row hull copies at a pitch that is W modulo 16.  Either way a lane's row r is
+//        `first row + r * pitch` at the alignment it has in global memory, read as aligned words + funnel shift.
 // CONTIG row loads with every shape known at compile time: WM = W & 7, A0 = alignment of the tile's row 0
 // (the same for every lane: tiles and bands are multiples of 8 bytes apart).  A row at byte alignment a is
 // one 8-byte load (a == 0), two 4-byte loads (a == 4), or an 8-byte and a 4-byte load of the three aligned
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
                 }
                 continue;
             }
-            if (CONTIG) {
+            if (CONTIG && g.nseg == 1) {
                 if (lane == 0) {
                     const uint8_t *g0 = fptr + (size_t)(8 * pi.y0) * g.W;
                     const uint32_t n = (uint32_t)min(nrows, g.H - 8 * pi.y0) * (uint32_t)g.W;
@@ -218,6 +218,34 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
                     mbar_arrive_expect_tx(&S.full[s], (uint32_t)(a1 - a0));
                     tma_load_1d(stage, (const void *)a0, (uint32_t)(a1 - a0), &S.full[s]);
                 }
+                continue;
+            }
+            if (CONTIG) {
+                // a band segment of an odd frame wider than 2048: its rows are not contiguous in the frame, so each
+                // row's 16-byte hull is copied on its own -- to a row pitch that is W modulo 16 (launch_encode), so that
+                // every row lands at its global alignment AND at a constant stride: the tile warps read it exactly
+                // like a contiguous partition (compile-time row shapes), only the stride differs.
+                const int rowbytes = min(8 * pi.ntx, g.W - 8 * pi.tx0);
+                const uint8_t *g0 = fptr + (size_t)(8 * pi.y0) * g.W + 8 * pi.tx0;
+                const uint32_t off0 = (uint32_t)((uintptr_t)g0 & 15);
+                const uint8_t *src = nullptr;
+                uint32_t len = 0, dst = 0;
+                if (lane < 8 && 8 * pi.y0 + lane < g.H) {
+                    const uint8_t *gr = g0 + (size_t)lane * g.W;
+                    const uintptr_t a0 = (uintptr_t)gr & ~(uintptr_t)15;
+                    const uintptr_t a1 = ((uintptr_t)gr + rowbytes + 15) & ~(uintptr_t)15;
+                    src = (const uint8_t *)a0;
+                    len = (uint32_t)(a1 - a0);
+                    dst = off0 + (uint32_t)lane * (uint32_t)g.pitch - (uint32_t)((uintptr_t)gr - a0);     // a multiple of 16
+                }
+                const uint32_t total = __reduce_add_sync(0xffffffffu, len);
+                if (lane == 0) {
+                    *reinterpret_cast<int4 *>(&S.ctl[s].part) = make_int4((int)p, pi.f, pi.tfirst, pi.nt);
+                    *reinterpret_cast<int4 *>(&S.ctl[s].q) = make_int4(pi.q, pi.y0, pi.tx0, (int)off0);
+                    mbar_arrive_expect_tx(&S.full[s], total);
+                }
+                __syncwarp();
+                if (len) tma_load_1d(stage + dst, src, len, &S.full[s]);
                 continue;
             }
             if (LIN) {
@@ -263,13 +291,11 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
                         const uintptr_t a1 = ((uintptr_t)a + rowbytes + 15) & ~(uintptr_t)15;
                         src[j] = (const uint8_t *)a0;
                         len[j] = (uint32_t)(a1 - a0);
-                        if (!FAST) S.ctl[s].rowoff[row] = (uint16_t)((uintptr_t)a - a0);
                     }
                 }
                 mybytes += len[j];
             }
             const uint32_t total = __reduce_add_sync(0xffffffffu, mybytes);
-            __syncwarp();               // every lane's rowoff[] store precedes the release below
             if (lane == 0) {
                 *reinterpret_cast<int4 *>(&S.ctl[s].part) = make_int4((int)p, pi.f, pi.tfirst, pi.nt);
                 *reinterpret_cast<int4 *>(&S.ctl[s].q) = make_int4(pi.q, pi.y0, pi.tx0, 0);
@@ -442,7 +468,7 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
             } else if (CONTIG) {
                 const int4 c1 = *reinterpret_cast<const int4 *>(&S.ctl[s].q);      // q, y0, tx0, first pixel's offset in the hull
                 const int rows_valid = min(8, g.H - 8 * (c1.y + sb));
-                const int ncol = min(8, g.W - 8 * stx);
+                const int ncol = min(8, g.W - 8 * (c1.z + stx));
                 uint32_t addr = smem_u32(stage) + (uint32_t)c1.w + (valid ? toff : 0u);      // idle lanes read (and discard) tile 0
                 auto load8 = [&](uint32_t a) {
                     uint32_t w0, w1, w2;
@@ -456,7 +482,7 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
                 // way -- the bytes past the row end are the next row's, or stage slack -- and then repeats its
                 // last valid pixel over them (dbde_util.cpp:119-127): one byte-broadcast and two selects per row.
                 if (!valid || rows_valid == 8) {
-                    load_rows_contig_any<WM>(addr, (uint32_t)g.W, px);
+                    load_rows_contig_any<WM>(addr, (uint32_t)g.pitch, px);
                     if (ncol < 8) {
                         const uint32_t bsel = 0x1111u * (uint32_t)(ncol - 1);                       // PRMT selector: byte ncol-1 of {lo, hi} four times
                         const uint32_t klo = ncol >= 4 ? 0xffffffffu : (1u << (8 * ncol)) - 1u;     // bytes of the low / high word that are real pixels
@@ -472,7 +498,7 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
                     // the frame's last band when H % 8 != 0: rows past H repeat the last valid row (dbde_util.cpp:111-117)
 #pragma unroll
                     for (int r = 0; r < 8; r++) {
-                        uint2 v = load8(addr + (uint32_t)(min(r, rows_valid - 1) * g.W));
+                        uint2 v = load8(addr + (uint32_t)(min(r, rows_valid - 1) * g.pitch));
                         if (ncol < 8) {
                             uint64_t x = ((uint64_t)v.y << 32) | v.x;
                             const uint64_t last = (x >> (8 * (ncol - 1))) & 0xffull;
@@ -483,29 +509,6 @@ __global__ void __launch_bounds__(kEncThreads, 3) dbde_encode_kernel(const EncPa
                         px[2 * r] = v.x;
                         px[2 * r + 1] = v.y;
                     }
-                }
-            } else {
-                // clamp-to-edge padding (dbde_util.cpp:105-135): rows past H repeat the last valid
-                // row, columns past W repeat the last valid pixel of the row
-                const int y0 = S.ctl[s].y0, tx0 = S.ctl[s].tx0;
-                const int rows_valid = min(8, g.H - 8 * (y0 + sb));
-                const int ncol = min(8, g.W - 8 * (tx0 + stx));
-#pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    uint2 v = make_uint2(0u, 0u);
-                    if (valid) {
-                        const int row = sb * 8 + min(r, rows_valid - 1);
-                        v = lds_u64_unaligned(stage + (size_t)row * g.pitch + S.ctl[s].rowoff[row] + stx * 8);
-                        if (ncol < 8) {
-                            uint64_t x = ((uint64_t)v.y << 32) | v.x;
-                            const uint64_t last = (x >> (8 * (ncol - 1))) & 0xffull;
-                            const uint64_t keep = (1ull << (8 * ncol)) - 1ull;
-                            x = (x & keep) | ((last * 0x0101010101010101ull) & ~keep);
-                            v = make_uint2((uint32_t)x, (uint32_t)(x >> 32));
-                        }
-                    }
-                    px[2 * r] = v.x;
-                    px[2 * r + 1] = v.y;
                 }
             }
             if (P.flags & kFlagInvertRows) reverse_rows(px);      // after the clamp padding, as ENDIAN() at dbde_util.cpp:24-27
@@ -646,13 +649,14 @@ cudaError_t launch_encode(const EncParams &Pin, bool fast, int num_sms, cudaStre
     EncParams P = Pin;
     const size_t smem = enc_smem_bytes(P.g);
     const bool wide = fast && (P.g.w % kTilesPerPart == 0) && P.g.pitch == kWidePitch;
-    const bool contig = !fast && P.g.nseg == 1;
-    if (contig) P.g.pitch = P.g.W;        // the stage holds the partition's pixels exactly as they lie in the frame
+    const bool contig = !fast;
+    // the stage holds the partition's pixels exactly as they lie in the frame (full-width partitions, pitch W), or
+    // a band segment's eight rows at a pitch that is W modulo 16 (wider frames; make_geom sized the stage for it)
+    if (contig && P.g.nseg == 1) P.g.pitch = P.g.W;
     void (*kern)(const EncParams) = nullptr;
     if (wide) kern = dbde_encode_kernel<true, true, false>;
     else if (fast && P.g.linear) kern = dbde_encode_kernel<true, false, false, 0, true>;
     else if (fast) kern = dbde_encode_kernel<true, false, false>;
-    else if (!contig) kern = dbde_encode_kernel<false, false, false>;
     else switch (P.g.W & 7) {
         case 0: kern = dbde_encode_kernel<false, false, true, 0>; break;
         case 1: kern = dbde_encode_kernel<false, false, true, 1>; break;

@@ -12,7 +12,8 @@ cs = torch.cuda.current_stream().cuda_stream
 rng = np.random.default_rng(1)
 cases = []
 for kind, W, H, Nmax in [("micro", 2048, 2048, 64), ("mix", 1001, 1003, 96), ("low", 4096, 4096, 16), ("mix", 264, 40, 512), ("noise", 2048, 512, 64),
-                         ("mix", 2049, 9, 64), ("micro", 13, 9, 2000)]:
+                         ("mix", 2049, 9, 64), ("micro", 13, 9, 2000), ("micro", 2304, 2304, 24), ("mix", 1280, 1024, 64),
+                         ("mix", 2560, 40, 200)]:
     px = W * H
     fr = torch.empty(Nmax * px + 64, dtype=torch.uint8, device=dev)
     synth.gen_frames_device(kind, Nmax, W, H, fr.data_ptr(), stream=cs)
