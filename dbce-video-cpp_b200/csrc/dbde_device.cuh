@@ -463,7 +463,7 @@ __device__ __forceinline__ void pack_low_depths(const uint32_t (&px)[16], int k,
     }
 }
 
-// unaligned-safe shared loads for the generic (odd width / odd offset) paths
+// unaligned-safe shared load for payloads that are not 8-byte aligned (records at odd offsets)
 __device__ __forceinline__ uint32_t lds_u32_unaligned(const uint8_t *p) {
     uint32_t a = smem_u32(p);
     const uint32_t *q = (const uint32_t *)(p - (a & 3u));
@@ -471,15 +471,6 @@ __device__ __forceinline__ uint32_t lds_u32_unaligned(const uint8_t *p) {
     uint32_t x0 = q[0];
     if (sh == 0) return x0;
     return __funnelshift_r(x0, q[1], sh);
-}
-__device__ __forceinline__ uint2 lds_u64_unaligned(const uint8_t *p) {
-    uint32_t a = smem_u32(p);
-    const uint32_t *q = (const uint32_t *)(p - (a & 3u));
-    uint32_t sh = (a & 3u) * 8u;
-    uint32_t x0 = q[0], x1 = q[1];
-    if (sh == 0) return make_uint2(x0, x1);
-    uint32_t x2 = q[2];
-    return make_uint2(__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh));
 }
 #endif  // __CUDACC__
 
