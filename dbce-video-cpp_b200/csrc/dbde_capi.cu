@@ -44,9 +44,23 @@ struct PhaseProfile {
     }
     const char *name[8] = {};
     double sum[8] = {};
+    double gpu[3] = {};                 // GPU timeline of the encode path: H2D DMAs, kernels, size copy + flag (ms)
+    cudaEvent_t ge[4] = {};
     long calls = 0;
     std::chrono::steady_clock::time_point t;
     void start() { if (on()) t = std::chrono::steady_clock::now(); }
+    void gpu_mark(int i, cudaStream_t st) {
+        if (!on()) return;
+        if (!ge[0]) for (auto &e : ge) cudaEventCreate(&e);
+        cudaEventRecord(ge[i], st);
+    }
+    void gpu_collect() {
+        if (!on() || !ge[0]) return;
+        for (int i = 0; i < 3; i++) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ge[i], ge[i + 1]) == cudaSuccess) gpu[i] += ms;
+        }
+    }
     void mark(int i, const char *what) {
         if (!on()) return;
         const auto n = std::chrono::steady_clock::now();
@@ -59,6 +73,8 @@ struct PhaseProfile {
         std::string line = "dbde_b200 profile (" + std::to_string(calls) + " calls, us per call):";
         for (int i = 0; i < 8; i++)
             if (name[i]) line += std::string(" ") + name[i] + "=" + std::to_string((long)(sum[i] / calls));
+        if (ge[0]) line += " | gpu: h2d=" + std::to_string((long)(1e3 * gpu[0] / calls)) + " kernels=" + std::to_string((long)(1e3 * gpu[1] / calls)) +
+                           " sizes+flag=" + std::to_string((long)(1e3 * gpu[2] / calls));
         fprintf(stderr, "%s\n", line.c_str());
     }
 };
@@ -507,6 +523,14 @@ void wait_flag_helping(volatile uint32_t *flag) {
 }
 }  // namespace
 
+static bool h2d_streaming() {
+    static const bool v = [] {
+        const char *e = getenv("DBDE_B200_H2D_STREAMING");
+        return !(e && e[0] == '0');
+    }();
+    return v;
+}
+
 static int ensure_bounce(dbde_b200_ctx *c, HostSlot &s, size_t need_in, size_t need_out) {
     if (need_in && s.cap_hin < need_in) {
         if (s.h_in) CK(cudaFreeHost(s.h_in));
@@ -554,7 +578,7 @@ static int relay_h2d(HostSlot &s, uint8_t *d_dst, const uint8_t *src, size_t n, 
     for (int i = 0; i < nj; i++) {
         const size_t o = (size_t)i * job;
         pend[i].store(1, std::memory_order_relaxed);
-        jobs[i] = CopyPool::Job{s.h_in + hoff + o, src + o, n - o < job ? n - o : job, &pend[i]};
+        jobs[i] = CopyPool::Job{s.h_in + hoff + o, src + o, n - o < job ? n - o : job, &pend[i], (uint8_t)(h2d_streaming() ? CopyPool::kStreamingStores : CopyPool::kPlain)};
     }
     pool.submit(jobs, nj);
     static const size_t dma_min = [] {
@@ -604,7 +628,7 @@ static void relay_d2h_collect(HostSlot &s, uint8_t *dst, size_t lo, size_t hi, s
         const size_t p0 = k * piece > lo ? k * piece : lo, p1 = (k + 1) * piece < hi ? (k + 1) * piece : hi;
         CopyPool::Job jobs[kMaxCopyJobs + 1];
         int nj = 0;
-        for (size_t q = p0; q < p1; q += job) jobs[nj++] = CopyPool::Job{dst + (q - lo), s.h_out + hoff + q, p1 - q < job ? p1 - q : job, &pend};
+        for (size_t q = p0; q < p1; q += job) jobs[nj++] = CopyPool::Job{dst + (q - lo), s.h_out + hoff + q, p1 - q < job ? p1 - q : job, &pend, (uint8_t)CopyPool::kPlain};
         pend.fetch_add(nj, std::memory_order_relaxed);
         pool.submit(jobs, nj);
     }
@@ -733,6 +757,7 @@ static int encode_host_worker(dbde_b200_ctx *c, const uint8_t *frames_host, int 
         if (in_pageable || out_pageable) wait_flag_helping(&s.h_flag[kFlagKernels]);    // copy (anyone's pieces) while waiting
         else CK(cudaEventSynchronize(s.ev));
         g_enc_prof.mark(3, "gpu");
+        g_enc_prof.gpu_collect();
         uint64_t total = 0;
         for (int i = 0; i < s.n; i++) total += s.h_size[i];
         while (seq->next.load(std::memory_order_acquire) != ci) {
@@ -768,6 +793,7 @@ static int encode_host_worker(dbde_b200_ctx *c, const uint8_t *frames_host, int 
         prof.mark(0, "setup");
         s.first = ci * chunk;
         s.n = nframes - s.first < chunk ? nframes - s.first : chunk;
+        prof.gpu_mark(0, s.st);
         if (in_pageable) {
             rc_all = relay_h2d(s, s.d_a, frames_host + px * s.first, px * s.n, 0);
             if (rc_all) break;
@@ -775,11 +801,13 @@ static int encode_host_worker(dbde_b200_ctx *c, const uint8_t *frames_host, int 
             CK(cudaMemcpyAsync(s.d_a, frames_host + px * s.first, px * s.n, cudaMemcpyHostToDevice, s.st));
         }
         prof.mark(1, "h2d");
+        prof.gpu_mark(1, s.st);
         rc_all = u16 ? dbde_b200_encode16_device(c, (const uint16_t *)s.d_a, W, H, first_index + s.first, s.n, s.d_b + delta,
                                                  need_b - 32, stride, s.d_off, s.d_size, s.st)
                      : dbde_b200_encode_device(c, s.d_a, W, H, first_index + s.first, s.n, s.d_b + delta, need_b - 32, stride,
                                                s.d_off, s.d_size, s.st);
         if (rc_all) break;
+        prof.gpu_mark(2, s.st);
         CK(cudaMemcpyAsync(s.h_size, s.d_size, 8 * (size_t)s.n, cudaMemcpyDeviceToHost, s.st));
         if (chunk > 1) {
             CK(launch_compact(s.d_b + delta, stride, s.d_size, s.n, s.d_c, s.st));
@@ -791,6 +819,7 @@ static int encode_host_worker(dbde_b200_ctx *c, const uint8_t *frames_host, int 
         } else {
             CK(cudaEventRecord(s.ev, s.st));
         }
+        prof.gpu_mark(3, s.st);
         prof.mark(2, "launch");
         if (pending >= 0) rc_all = finish(pending);
         pending = li;

@@ -21,24 +21,52 @@ bool dbde_advance_file_buffer(dbde_file_walker &w);      // exported by the refe
 
 namespace {
 
-// One lazily created context per calling thread: keeps the reference's "re-entrant, callable
-// from several threads on disjoint buffers" property without a global lock.
+// One context per calling thread, lazily taken: keeps the reference's "re-entrant, callable from several
+// threads on disjoint buffers" property without a global lock.  A thread that ends does NOT
+// destroy its context -- freeing device and page-locked memory takes the driver's global lock for hundreds of
+// milliseconds, and every other thread's next CUDA call waits behind it (measured: callers that finished early
+// stalled the remaining dbde_unpack_frame callers for 0.3-1.3 s per call, 6 k -> 100 frames/s) -- it parks the
+// context in a process-wide pool, where the next new thread finds it warm.  The pool is emptied at process exit.
+struct ContextPool {
+    std::mutex m;
+    std::vector<dbde_b200_ctx *> idle;
+    ~ContextPool() {
+        for (dbde_b200_ctx *c : idle) dbde_b200_destroy(c);
+    }
+    static ContextPool &get() {
+        static ContextPool p;
+        return p;
+    }
+};
 struct ThreadCtx {
     dbde_b200_ctx *ctx = nullptr;
     ~ThreadCtx() {
-        if (ctx) dbde_b200_destroy(ctx);
+        if (!ctx) return;
+        ContextPool &p = ContextPool::get();
+        std::lock_guard<std::mutex> lk(p.m);
+        p.idle.push_back(ctx);
     }
 };
 
 dbde_b200_ctx *ctx() {
     static thread_local ThreadCtx t;
     if (!t.ctx) {
-        const char *dev = getenv("DBDE_B200_DEVICE");
-        int rc = dbde_b200_create(dev ? atoi(dev) : 0, &t.ctx);
-        if (rc != 0 || !t.ctx) {
-            // there is no CPU fallback: the drop-in signatures cannot report this, so stop loudly
-            fprintf(stderr, "dbde_b200: cannot create a GPU context (%d): %s\n", rc, dbde_b200_last_error());
-            abort();
+        {
+            ContextPool &p = ContextPool::get();
+            std::lock_guard<std::mutex> lk(p.m);
+            if (!p.idle.empty()) {
+                t.ctx = p.idle.back();
+                p.idle.pop_back();
+            }
+        }
+        if (!t.ctx) {
+            const char *dev = getenv("DBDE_B200_DEVICE");
+            int rc = dbde_b200_create(dev ? atoi(dev) : 0, &t.ctx);
+            if (rc != 0 || !t.ctx) {
+                // there is no CPU fallback: the drop-in signatures cannot report this, so stop loudly
+                fprintf(stderr, "dbde_b200: cannot create a GPU context (%d): %s\n", rc, dbde_b200_last_error());
+                abort();
+            }
         }
     }
     int inv = 0;
@@ -64,23 +92,54 @@ void die(const char *what, int rc) {
 struct ScratchRecord {
     uint8_t *p = nullptr;
     size_t cap = 0;
-    ~ScratchRecord() {
-        if (p) dbde_b200_host_free(p);
+};
+struct ScratchPool {                 // like ContextPool: a thread that ends parks its page-locked scratch, it does not free it
+    std::mutex m;
+    std::vector<ScratchRecord> idle;
+    ~ScratchPool() {
+        for (ScratchRecord &r : idle)
+            if (r.p) dbde_b200_host_free(r.p);
+    }
+    static ScratchPool &get() {
+        static ScratchPool p;
+        return p;
+    }
+};
+struct ThreadScratch {
+    ScratchRecord r;
+    ~ThreadScratch() {
+        if (!r.p) return;
+        ScratchPool &p = ScratchPool::get();
+        std::lock_guard<std::mutex> lk(p.m);
+        p.idle.push_back(r);
     }
 };
 uint8_t *scratch_record(size_t bytes) {
-    static thread_local ScratchRecord r;
+    static thread_local ThreadScratch t;
+    ScratchRecord &r = t.r;
     if (r.cap < bytes) {
-        if (r.p) dbde_b200_host_free(r.p);
-        r.p = nullptr;
-        r.cap = 0;
-        void *q = nullptr;
-        if (dbde_b200_host_alloc(bytes + bytes / 4, &q) != 0 || !q) {
-            fprintf(stderr, "dbde_b200: cannot allocate %zu bytes of page-locked scratch: %s\n", bytes, dbde_b200_last_error());
-            abort();
+        ScratchPool &pool = ScratchPool::get();
+        {
+            std::lock_guard<std::mutex> lk(pool.m);
+            if (r.p) pool.idle.push_back(r);           // too small for this geometry: somebody else may still use it
+            r = ScratchRecord();
+            for (size_t i = 0; i < pool.idle.size(); i++)
+                if (pool.idle[i].cap >= bytes) {
+                    r = pool.idle[i];
+                    pool.idle[i] = pool.idle.back();
+                    pool.idle.pop_back();
+                    break;
+                }
         }
-        r.p = (uint8_t *)q;
-        r.cap = bytes + bytes / 4;
+        if (!r.p) {
+            void *q = nullptr;
+            if (dbde_b200_host_alloc(bytes + bytes / 4, &q) != 0 || !q) {
+                fprintf(stderr, "dbde_b200: cannot allocate %zu bytes of page-locked scratch: %s\n", bytes, dbde_b200_last_error());
+                abort();
+            }
+            r.p = (uint8_t *)q;
+            r.cap = bytes + bytes / 4;
+        }
     }
     return r.p;
 }

@@ -42,7 +42,7 @@ int main(int argc, char **argv) {
                 for (int i = 0; i < nj; i++) {
                     const size_t o = (size_t)i * job;
                     pend[i].store(1);
-                    jobs[i] = CopyPool::Job{bounce.data() + o, src.data() + o, n - o < job ? n - o : job, &pend[i]};
+                    jobs[i] = CopyPool::Job{bounce.data() + o, src.data() + o, n - o < job ? n - o : job, &pend[i], (uint8_t)((r & 1) ? CopyPool::kStreamingStores : CopyPool::kPlain)};
                 }
                 pool.submit(jobs, nj);
                 for (int i = 0; i < nj; i++) pool.help_until([&] { return pend[i].load(std::memory_order_acquire) == 0; });
