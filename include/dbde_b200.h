@@ -16,6 +16,18 @@
  * All functions return 0 on success or a negative dbde_b200_error / positive cudaError_t value;
  * dbde_b200_last_error() describes the last failure on the calling thread.  There is NO CPU
  * fallback: without a CUDA device of compute capability 10.x every call fails loudly.
+ *
+ * Environment (all optional; read once unless noted):
+ *   DBDE_B200_DEVICE          device the C++ drop-in functions use (default 0)
+ *   DBDE_B200_SLOTS           staging slots in flight on the host path, 2..8 (default 3)
+ *   DBDE_B200_CHUNK_FRAMES    frames per staged chunk (default: 64 MiB of pixels)
+ *   DBDE_B200_COPY_THREADS    size of the pool that relays pageable buffers (default min(6, cores/2 - 1))
+ *   DBDE_B200_COPY_CROWD      calling threads helping at once from which the pool stands back (default cores/2)
+ *   DBDE_B200_H2D_DMA_KB / DBDE_B200_D2H_DMA_KB   smallest DMA on the pageable path (default 1024)
+ *   DBDE_B200_H2D_STREAMING=0 ordinary instead of streaming stores into the bounce buffers
+ *   DBDE_B200_PROFILE=1       per-thread phase times of the host path on stderr when a thread ends
+ *   measurement switches, read per call: DBDE_B200_ODD_DECODE=staged|direct (odd-size unpack kernel),
+ *   DBDE_B200_NO_LINEAR=1 (band-aligned partitions for every aligned frame)
  */
 #ifndef DBDE_B200_H
 #define DBDE_B200_H
