@@ -983,3 +983,35 @@ def test_file_api_follows_the_hz_as_integer_variant(codec, dropin):
                 assert (W, H, hz) == (200, 96, 30.0 if hz_int else 29.97) and (got == fr).all() and (st == 0).all()
             finally:
                 pkg.set_format_variants(False, False)
+
+
+def test_drop_in_functions_from_many_short_lived_threads(dropin):
+    """the reference's functions are re-entrant, so callers use them from threads that come and go:
+    three waves of eight threads, each packing and unpacking its own frames through the C++ symbols on numpy
+    (pageable) buffers -- the copy pool's helping waits, the completion flags and the context pool (a thread that
+    ends parks its GPU context, the next wave picks the warm ones up) under real CUDA traffic; every record must be
+    the reference's and every image must come back"""
+    import threading
+    W, H = 520, 264
+    errors = []
+
+    def worker(seed):
+        try:
+            rng = np.random.default_rng(seed)
+            for i in range(4):
+                img = rand_frame(rng, W, H, ["classes", "noise", "flat"][(seed + i) % 3])
+                rec = dropin.pack_frame(1000 * seed + i, img)
+                want, _ = ORA.pack_frames(img[None], 1000 * seed + i)
+                assert (rec == want).all(), (seed, i)
+                used, (u64s, index, _), back = dropin.unpack_frame(rec, W, H)
+                assert used == len(rec) and u64s == 2 and index == 1000 * seed + i and (back == img).all(), (seed, i)
+        except Exception as e:           # noqa: BLE001 -- reported by the main thread
+            errors.append(repr(e))
+
+    for wave in range(3):
+        ts = [threading.Thread(target=worker, args=(8 * wave + t,)) for t in range(8)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+    assert not errors, errors[:3]
