@@ -2,19 +2,24 @@
 // dbde_unpack_frame (dbde_util.cpp:339-345) and with its accept/reject behaviour
 // (dbde_util.cpp:295-303: a rejected frame leaves the image untouched).
 //
-// Two kernels:
-//   dbde_decode_scan_kernel : one CTA per frame. Validates the record (header tag, plane lengths,
-//                             sum(depth) == n64, depth <= 8, bounds) and turns the depth plane into
-//                             exclusive U64-word prefixes at partition-warp granularity (32 tiles),
-//                             i.e. the reference's running input pointer (dbde_util.cpp:312) made
-//                             explicit.  Reads 1 byte per tile (~1 % of the traffic).
-//   dbde_decode_kernel      : persistent, warp-specialised.  A producer warp bulk-TMAs each
-//                             partition's payload words + depth/min bytes into a ring of stages;
-//                             tile warps (one lane == one 8x8 tile) unpack with shifts and masks,
-//                             add the minimum and store their rows straight from registers: a
-//                             warp's 32 tiles make each row store one coalesced 256-byte segment,
-//                             so the warps never synchronise with each other (generic path:
-//                             cropped stores).
+// Three kernels:
+//   dbde_decode_scan_kernel   : one CTA per frame. Validates the record (header tag, plane lengths,
+//                               sum(depth) == n64, depth <= 8, bounds) and turns the depth plane into
+//                               exclusive U64-word prefixes at partition-warp granularity (32 tiles),
+//                               i.e. the reference's running input pointer (dbde_util.cpp:312) made
+//                               explicit.  Reads 1 byte per tile (~1 % of the traffic).
+//   dbde_decode_kernel<MODE>  : persistent, warp-specialised.  A producer warp bulk-TMAs each
+//                               partition's payload words + depth/min bytes into a ring of stages;
+//                               tile warps (one lane == one 8x8 tile) unpack with shifts and masks,
+//                               add the minimum and store their rows straight from registers: a
+//                               warp's 32 tiles make each row store one coalesced 256-byte segment,
+//                               so the warps never synchronise with each other.  MODE -1: aligned
+//                               frames; -2: aligned frames with linear partitions; 0..7 = W & 7: odd
+//                               geometries, rows re-aligned across lanes with compile-time shapes
+//                               (what odd frames wider than 2048 run).
+//   dbde_decode_staged_kernel<WM> : odd frames whose partitions span the full width (W <= 2048): the
+//                               partition's pixels are built in shared memory as they lie in the frame
+//                               (compile-time row shapes) and leave with one bulk-TMA store.
 #include "dbde_device.cuh"
 #include "dbde_kernels.h"
 #include <stdlib.h>
