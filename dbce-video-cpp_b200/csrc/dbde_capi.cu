@@ -599,22 +599,30 @@ static int relay_h2d(HostSlot &s, uint8_t *d_dst, const uint8_t *src, size_t n, 
 
 // device -> the slot's pinned h_out (at offset hoff), in DMA pieces with one completion flag each, queued on
 // the slot's stream.  Returns the piece size; pieces k = 0 .. ceil(n / piece) - 1 report on h_flag[k].
-static int relay_d2h_enqueue(dbde_b200_ctx *c, HostSlot &s, const uint8_t *d_src, size_t n, size_t hoff, size_t *piece_out) {
+// the DMA piece size for relaying up to n bytes (at most kMaxDmaPieces pieces, one completion flag each)
+static size_t d2h_piece_bytes(size_t n) {
     static const size_t piece_min = [] {
         const char *e = getenv("DBDE_B200_D2H_DMA_KB");
         return (size_t)(e && atoi(e) > 0 ? atoi(e) : 1024) << 10;
     }();
     size_t piece = piece_min;
     while ((n + piece - 1) / piece > (size_t)kMaxDmaPieces) piece *= 2;
-    const int np = (int)((n + piece - 1) / piece);
-    for (int k = 0; k < np; k++) {
+    return piece;
+}
+// pieces k_first, k_first + 1, ... of the first n bytes at d_src, each to its place in h_out and each followed by its flag
+static int relay_d2h_enqueue_from(dbde_b200_ctx *c, HostSlot &s, const uint8_t *d_src, size_t n, size_t hoff, size_t piece,
+                                  int k_first) {
+    for (int k = k_first; (size_t)k * piece < n; k++) {
         const size_t o = (size_t)k * piece;
         CK(cudaMemcpyAsync(s.h_out + hoff + o, d_src + o, n - o < piece ? n - o : piece, cudaMemcpyDeviceToHost, s.st));
         int rc = signal_flag(c, s, k);
         if (rc) return rc;
     }
-    *piece_out = piece;
     return 0;
+}
+static int relay_d2h_enqueue(dbde_b200_ctx *c, HostSlot &s, const uint8_t *d_src, size_t n, size_t hoff, size_t *piece_out) {
+    *piece_out = d2h_piece_bytes(n);
+    return relay_d2h_enqueue_from(c, s, d_src, n, hoff, *piece_out, 0);
 }
 // ... and out of h_out into pageable memory as the pieces land: bytes [lo, hi) of the n relayed bytes go to
 // dst + (their offset - lo).  Pieces are copied out by the pool and the waiting callers while later pieces
@@ -748,6 +756,9 @@ static int encode_host_worker(dbde_b200_ctx *c, const uint8_t *frames_host, int 
         if (rc) return rc;
     }
     const size_t stride = F.stride;
+    // One frame per call into pageable memory (the drop-in functions): the record's size is not known until the
+    // kernel has run, but its first DMA piece can follow the kernel at once -- most records are longer than a piece.
+    const size_t spec_piece = (chunk == 1 && out_pageable) ? d2h_piece_bytes(stride) : 0;
     // finish(): wait for a chunk's kernels, learn the record sizes, claim the chunk's place in the
     // stream, and queue ONE D2H copy of its records -- already laid back to back on the device
     // (a one-frame chunk's record is contiguous in its slot as it is: no compaction pass).
@@ -774,6 +785,17 @@ static int encode_host_worker(dbde_b200_ctx *c, const uint8_t *frames_host, int 
             run += s.h_size[i];
         }
         const uint8_t *d_rec = chunk > 1 ? s.d_c : s.d_b + delta;
+        if (out_pageable && spec_piece) {
+            // the record's first piece has been on its way since the kernel was queued; now that the size is known
+            // the remaining pieces follow, and everything up to `total` leaves the bounce buffer
+            int rc = relay_d2h_enqueue_from(c, s, d_rec, total, 0, spec_piece, 1);
+            if (rc) return rc;
+            std::atomic<int> pend{0};
+            relay_d2h_collect(s, out_host + pos, 0, total, total, spec_piece, 0, pend);
+            CopyPool::get().help_until([&] { return pend.load(std::memory_order_acquire) == 0; });
+            g_enc_prof.mark(4, "d2h");
+            return 0;
+        }
         if (out_pageable) {
             const int rc = relay_d2h(c, s, out_host + pos, d_rec, total, 0);
             g_enc_prof.mark(4, "d2h");
@@ -815,6 +837,8 @@ static int encode_host_worker(dbde_b200_ctx *c, const uint8_t *frames_host, int 
         }
         if (in_pageable || out_pageable) {
             rc_all = signal_flag(c, s, kFlagKernels);
+            if (!rc_all && spec_piece)
+                rc_all = relay_d2h_enqueue_from(c, s, s.d_b + delta, spec_piece < stride ? spec_piece : stride, 0, spec_piece, 0);
             if (rc_all) break;
         } else {
             CK(cudaEventRecord(s.ev, s.st));
